@@ -1,0 +1,120 @@
+/*
+ * snappy_b200.h -- C-ABI of libsnappy_b200.so, the B200-native (sm_100a) Snappy block
+ * codec that sits behind the C API of tturturiello/lightweight-snappy.
+ *
+ * Three layers, all `extern "C"`, plain pointers and sizes:
+ *
+ *   1. device-level batched API   (this file; DEVICE pointers, asynchronous on a stream)
+ *   2. host-buffer API            (this file; HOST pointers, staging + copies inside)
+ *   3. the reference's own symbols (snappy_compression.h, snappy_compression_tree.h,
+ *      snappy_decompression.h, varint.h, buffer_compression.h in this directory):
+ *      same names, signatures and stream format as the reference headers, so cmd.c-style
+ *      callers relink unchanged.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference repo):
+ *   snappy_b200_compress_device / _host, MODE_HASH -> the per-block loop of
+ *        src/snappy_compression.c:384-403 driven by snappy_compress :414-428
+ *   snappy_b200_compress_device / _host, MODE_BST  -> src/snappy_compression_tree.c:269-288
+ *        driven by snappy_compress_bst :291-306 (exact-key dictionary of src/BST.c)
+ *   snappy_b200_decompress_device* / _host          -> src/snappy_decompression.c:345-363
+ *        (element loop :290-333, literal :193-239, copy :253-280)
+ *   snappy_b200_index_device                        -> the block boundaries that the
+ *        sequential loop at src/snappy_decompression.c:353-356 discovers implicitly
+ *   varint preamble                                 -> src/varint.c:12-20 / :28-58
+ *
+ * Stream format (identical to the reference): LEB128(total uncompressed bytes) followed
+ * by the compressed 64 KiB blocks, concatenated with no framing.  An empty input gives an
+ * empty stream (the reference never flushes the varint).
+ *
+ * There is no CPU fallback: every call fails with SNAPPY_B200_ERR_CUDA when no usable
+ * sm_100 device / driver is present.
+ */
+#ifndef SNAPPY_B200_H
+#define SNAPPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNAPPY_B200_BLOCK_SIZE 65536u  /* MAX_BLOCK_SIZE, src/snappy_compression.c:9 */
+#define SNAPPY_B200_HTABLE_SIZE 4096u  /* MAX_HTABLE_SIZE, src/snappy_compression.c:10 */
+#define SNAPPY_B200_SLOT_STRIDE 66560u /* per-block scratch slot: 65536 + 1010 (+pad), :180-190 */
+
+#define SNAPPY_B200_MODE_HASH 0 /* src/snappy_compression.c */
+#define SNAPPY_B200_MODE_BST 1  /* src/snappy_compression_tree.c */
+
+#define SNAPPY_B200_OK 0
+#define SNAPPY_B200_ERR_CUDA (-1)     /* CUDA runtime / driver error, or no device */
+#define SNAPPY_B200_ERR_ARG (-2)      /* bad argument (null, misaligned, too small) */
+#define SNAPPY_B200_ERR_CAPACITY (-3) /* output buffer too small */
+#define SNAPPY_B200_ERR_CORRUPT (-4)  /* malformed compressed stream */
+#define SNAPPY_B200_ERR_FRAMING (-5)  /* valid Snappy, but an element straddles a 64 KiB block */
+#define SNAPPY_B200_ERR_IO (-6)       /* FILE* read/write failed (drop-in layer) */
+
+/* Status word written by the device kernels (bit set; 0 = clean). */
+#define SNAPPY_B200_ST_CAPACITY 1u
+#define SNAPPY_B200_ST_CORRUPT 2u
+#define SNAPPY_B200_ST_FRAMING 4u
+#define SNAPPY_B200_ST_UNRESOLVED 8u /* internal: the stream index did not converge */
+
+/* Message of the last failing call on this thread (never NULL). */
+const char *snappy_b200_last_error(void);
+/* Number of CUDA devices visible, or a negative SNAPPY_B200_ERR_CUDA. */
+int snappy_b200_device_count(void);
+/* How many kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t snappy_b200_launch_count(void);
+
+/* Upper bound of the stream for n input bytes: 10 + n + 1010 per block (src :180-190). */
+uint64_t snappy_b200_max_compressed_bytes(uint64_t n_bytes);
+uint64_t snappy_b200_block_count(uint64_t n_bytes);
+
+/* ---------------------------------------------------------------- 1. device-level API
+ * All pointers are device pointers on the current device, 16-byte aligned unless noted.
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls only enqueue
+ * work; results (including *d_status) are valid after the stream is synchronised.       */
+
+size_t snappy_b200_compress_workspace_bytes(uint64_t n_bytes, int mode);
+
+/* Compresses n_bytes at d_in into one reference-format stream at d_out.
+ *   d_out_bytes      [1]  total stream length (varint + blocks)
+ *   d_block_offsets  [n_blocks+1] (optional, may be NULL) stream offset of every block --
+ *                    the side index a later indexed decode can reuse; entry n_blocks =
+ *                    stream length
+ *   d_status         [1]  SNAPPY_B200_ST_* bits (CAPACITY when out_capacity was too small) */
+int snappy_b200_compress_device(const uint8_t *d_in, uint64_t n_bytes, int mode, uint8_t *d_out,
+                                uint64_t out_capacity, uint64_t *d_out_bytes, uint64_t *d_block_offsets,
+                                uint32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Decodes n_blocks blocks whose stream offsets are given (d_block_offsets[n_blocks+1]);
+ * block i produces bytes [i*65536, min(total_out, (i+1)*65536)) of d_out.               */
+int snappy_b200_decompress_device_indexed(const uint8_t *d_stream, const uint64_t *d_block_offsets,
+                                          uint64_t n_blocks, uint64_t total_out, uint8_t *d_out,
+                                          uint32_t *d_status, void *stream);
+
+size_t snappy_b200_index_workspace_bytes(uint64_t stream_bytes);
+
+/* Finds the block boundaries of an index-less stream body (the bytes after the varint):
+ * d_block_offsets[n_blocks+1] receives offsets relative to d_stream (which must point at
+ * the start of the whole stream; body_offset = length of the varint).                   */
+int snappy_b200_index_device(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
+                             uint64_t total_out, uint64_t *d_block_offsets, uint32_t *d_status,
+                             void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------- 2. host-buffer API
+ * Synchronous.  Host pointers (pageable or pinned); staging through pinned buffers and
+ * the host<->device copies happen inside.                                               */
+int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
+                              uint64_t *out_bytes);
+int snappy_b200_uncompressed_length(const void *stream, uint64_t stream_bytes, uint64_t *n_bytes);
+int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void *out, uint64_t out_capacity,
+                                uint64_t *out_bytes);
+/* Releases the cached device/pinned buffers of the host-buffer API. */
+void snappy_b200_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNAPPY_B200_H */

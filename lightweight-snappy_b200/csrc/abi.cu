@@ -1,0 +1,376 @@
+// abi.cu -- the C-ABI of libsnappy_b200.so (see include/snappy_b200.h): argument checks,
+// workspace carving, kernel sequencing, and the synchronous host-buffer entry points.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace sb200 {
+cudaError_t launch_compress(const uint8_t *, uint64_t, int, uint8_t *, uint32_t *, cudaStream_t, uint64_t *);
+cudaError_t launch_compact(const uint8_t *, const uint32_t *, uint64_t, uint64_t, uint64_t, int, uint8_t *, uint64_t,
+                           uint64_t *, uint64_t *, uint32_t *, cudaStream_t, uint64_t *);
+cudaError_t launch_decode(const uint8_t *, const uint64_t *, uint64_t, uint64_t, uint8_t *, uint32_t *, cudaStream_t,
+                          uint64_t *);
+size_t index_workspace_bytes(uint64_t);
+cudaError_t run_index(const uint8_t *, uint64_t, uint64_t, uint64_t, uint64_t *, uint32_t *, void *, cudaStream_t,
+                      uint64_t *);
+uint32_t host_varint_len(uint64_t);
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(SNAPPY_B200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct CompressWorkspace {
+    uint8_t *scratch;
+    uint32_t *sizes;
+    uint64_t *offsets;
+};
+
+static size_t compress_ws_bytes(uint64_t n_bytes)
+{
+    const uint64_t nb = (n_bytes + kBlock - 1) / kBlock;
+    return align_up(nb * (size_t)kSlot + 64, 256) + align_up(nb * 4 + 4, 256) + align_up((nb + 1) * 8, 256);
+}
+
+static CompressWorkspace carve_compress(void *ws, uint64_t n_bytes)
+{
+    const uint64_t nb = (n_bytes + kBlock - 1) / kBlock;
+    uint8_t *p = static_cast<uint8_t *>(ws);
+    CompressWorkspace w;
+    w.scratch = p, p += align_up(nb * (size_t)kSlot + 64, 256);
+    w.sizes = reinterpret_cast<uint32_t *>(p), p += align_up(nb * 4 + 4, 256);
+    w.offsets = reinterpret_cast<uint64_t *>(p);
+    return w;
+}
+
+static int status_to_error(uint32_t st)
+{
+    if (st & SNAPPY_B200_ST_CORRUPT)
+        return fail(SNAPPY_B200_ERR_CORRUPT, "malformed compressed stream (device status 0x%x)", st);
+    if (st & SNAPPY_B200_ST_FRAMING)
+        return fail(SNAPPY_B200_ERR_FRAMING, "an element straddles a 64 KiB block (device status 0x%x)", st);
+    if (st & SNAPPY_B200_ST_CAPACITY)
+        return fail(SNAPPY_B200_ERR_CAPACITY, "output buffer too small (device status 0x%x)", st);
+    if (st)
+        return fail(SNAPPY_B200_ERR_CORRUPT, "device status 0x%x", st);
+    return SNAPPY_B200_OK;
+}
+
+} // namespace sb200
+
+using namespace sb200;
+
+extern "C" {
+
+const char *snappy_b200_last_error(void) { return g_err; }
+
+int snappy_b200_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "cudaGetDeviceCount");
+    return n;
+}
+
+uint64_t snappy_b200_launch_count(void) { return g_launches.load(); }
+
+uint64_t snappy_b200_block_count(uint64_t n_bytes) { return (n_bytes + kBlock - 1) / kBlock; }
+
+uint64_t snappy_b200_max_compressed_bytes(uint64_t n_bytes)
+{
+    return n_bytes ? 10 + n_bytes + snappy_b200_block_count(n_bytes) * 1010 : 0;
+}
+
+size_t snappy_b200_compress_workspace_bytes(uint64_t n_bytes, int mode)
+{
+    (void)mode;
+    return compress_ws_bytes(n_bytes);
+}
+
+int snappy_b200_compress_device(const uint8_t *d_in, uint64_t n_bytes, int mode, uint8_t *d_out, uint64_t out_capacity,
+                                uint64_t *d_out_bytes, uint64_t *d_block_offsets, uint32_t *d_status,
+                                void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (mode != SNAPPY_B200_MODE_HASH && mode != SNAPPY_B200_MODE_BST)
+        return fail(SNAPPY_B200_ERR_ARG, "unknown mode %d", mode);
+    if (!d_out_bytes || !d_status || (n_bytes && (!d_in || !d_out || !d_workspace)))
+        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    if (!aligned16(d_in) || !aligned16(d_out) || !aligned16(d_workspace))
+        return fail(SNAPPY_B200_ERR_ARG, "d_in, d_out and d_workspace must be 16-byte aligned");
+    if (workspace_bytes < compress_ws_bytes(n_bytes))
+        return fail(SNAPPY_B200_ERR_ARG, "workspace too small: %zu < %zu", workspace_bytes, compress_ws_bytes(n_bytes));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint64_t nb = (n_bytes + kBlock - 1) / kBlock;
+    cudaError_t e = cudaMemsetAsync(d_status, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "cudaMemsetAsync(status)");
+    if (nb == 0) { // reference: an empty input gives an empty stream
+        e = cudaMemsetAsync(d_out_bytes, 0, sizeof(uint64_t), st);
+        if (e == cudaSuccess && d_block_offsets)
+            e = cudaMemsetAsync(d_block_offsets, 0, sizeof(uint64_t), st);
+        return e == cudaSuccess ? SNAPPY_B200_OK : cuda_fail(e, "cudaMemsetAsync");
+    }
+    CompressWorkspace w = carve_compress(d_workspace, n_bytes);
+    uint64_t launches = 0;
+    e = launch_compress(d_in, n_bytes, mode, w.scratch, w.sizes, st, &launches);
+    if (e == cudaSuccess)
+        e = launch_compact(w.scratch, w.sizes, nb, n_bytes, host_varint_len(n_bytes), 1, d_out, out_capacity,
+                           d_block_offsets ? d_block_offsets : w.offsets, d_out_bytes, d_status, st, &launches);
+    g_launches += launches;
+    if (e != cudaSuccess)
+        return cuda_fail(e, "compress launch");
+    return SNAPPY_B200_OK;
+}
+
+int snappy_b200_decompress_device_indexed(const uint8_t *d_stream, const uint64_t *d_block_offsets, uint64_t n_blocks,
+                                          uint64_t total_out, uint8_t *d_out, uint32_t *d_status, void *stream)
+{
+    if (!d_status || (n_blocks && (!d_stream || !d_block_offsets || !d_out)))
+        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    if (n_blocks != (total_out + kBlock - 1) / kBlock)
+        return fail(SNAPPY_B200_ERR_ARG, "n_blocks does not match total_out");
+    uint64_t launches = 0;
+    cudaError_t e = launch_decode(d_stream, d_block_offsets, n_blocks, total_out, d_out, d_status,
+                                  static_cast<cudaStream_t>(stream), &launches);
+    g_launches += launches;
+    if (e != cudaSuccess)
+        return cuda_fail(e, "decode launch");
+    return SNAPPY_B200_OK;
+}
+
+size_t snappy_b200_index_workspace_bytes(uint64_t stream_bytes) { return index_workspace_bytes(stream_bytes); }
+
+int snappy_b200_index_device(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset, uint64_t total_out,
+                             uint64_t *d_block_offsets, uint32_t *d_status, void *d_workspace, size_t workspace_bytes,
+                             void *stream)
+{
+    if (!d_stream || !d_block_offsets || !d_status || !d_workspace)
+        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    if (body_offset > stream_bytes || stream_bytes >= (1ull << 40))
+        return fail(SNAPPY_B200_ERR_ARG, "bad stream size / body offset");
+    if (workspace_bytes < index_workspace_bytes(stream_bytes))
+        return fail(SNAPPY_B200_ERR_ARG, "workspace too small");
+    uint64_t launches = 0;
+    cudaError_t e = run_index(d_stream, stream_bytes, body_offset, total_out, d_block_offsets, d_status, d_workspace,
+                              static_cast<cudaStream_t>(stream), &launches);
+    g_launches += launches;
+    if (e != cudaSuccess)
+        return cuda_fail(e, "index launch");
+    return SNAPPY_B200_OK;
+}
+
+} // extern "C"
+
+// ----------------------------------------------------------------------------- host-buffer API
+namespace sb200 {
+
+// Cached per-process buffers of the synchronous host-buffer entry points.
+struct HostCtx {
+    std::mutex mu;
+    cudaStream_t st = nullptr;
+    void *buf[4] = {nullptr, nullptr, nullptr, nullptr}; // 0 in, 1 out, 2 workspace, 3 small (offsets etc.)
+    size_t cap[4] = {0, 0, 0, 0};
+    uint64_t *h_small = nullptr; // pinned: [0] out_bytes, [1] status
+
+    cudaError_t need(int i, size_t bytes)
+    {
+        bytes = align_up(bytes + 256, 1 << 20);
+        if (cap[i] >= bytes)
+            return cudaSuccess;
+        if (buf[i])
+            cudaFree(buf[i]);
+        buf[i] = nullptr;
+        cap[i] = 0;
+        cudaError_t e = cudaMalloc(&buf[i], bytes);
+        if (e == cudaSuccess)
+            cap[i] = bytes;
+        return e;
+    }
+    cudaError_t init()
+    {
+        cudaError_t e = cudaSuccess;
+        if (!st)
+            e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (e == cudaSuccess && !h_small)
+            e = cudaHostAlloc(reinterpret_cast<void **>(&h_small), 64, cudaHostAllocDefault);
+        return e;
+    }
+    void release()
+    {
+        for (int i = 0; i < 4; ++i) {
+            if (buf[i])
+                cudaFree(buf[i]);
+            buf[i] = nullptr;
+            cap[i] = 0;
+        }
+        if (h_small)
+            cudaFreeHost(h_small);
+        h_small = nullptr;
+        if (st)
+            cudaStreamDestroy(st);
+        st = nullptr;
+    }
+};
+
+static HostCtx g_ctx;
+
+static unsigned host_varint_decode(const uint8_t *p, uint64_t avail, uint64_t *out)
+{
+    uint64_t v = 0;
+    unsigned shift = 0;
+    for (unsigned k = 0; k < avail && k < 10; ++k) {
+        v |= (uint64_t)(p[k] & 0x7fu) << shift;
+        shift += 7;
+        if (!(p[k] & 0x80u)) {
+            *out = v;
+            return k + 1;
+        }
+    }
+    return 0;
+}
+
+} // namespace sb200
+
+extern "C" {
+
+int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
+                              uint64_t *out_bytes)
+{
+    if (!out_bytes || (n_bytes && (!in || !out)))
+        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    *out_bytes = 0;
+    if (n_bytes == 0)
+        return SNAPPY_B200_OK;
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    cudaError_t e = g_ctx.init();
+    if (e != cudaSuccess)
+        return cuda_fail(e, "context init");
+    const uint64_t nb = (n_bytes + kBlock - 1) / kBlock;
+    const uint64_t max_out = snappy_b200_max_compressed_bytes(n_bytes);
+    const size_t ws_bytes = compress_ws_bytes(n_bytes);
+    if ((e = g_ctx.need(0, n_bytes)) != cudaSuccess || (e = g_ctx.need(1, max_out)) != cudaSuccess ||
+        (e = g_ctx.need(2, ws_bytes)) != cudaSuccess || (e = g_ctx.need(3, (nb + 1) * 8 + 64)) != cudaSuccess)
+        return cuda_fail(e, "cudaMalloc");
+    uint8_t *d_in = static_cast<uint8_t *>(g_ctx.buf[0]);
+    uint8_t *d_out = static_cast<uint8_t *>(g_ctx.buf[1]);
+    uint64_t *d_small = static_cast<uint64_t *>(g_ctx.buf[3]); // [0] out_bytes, [1] status
+    cudaStream_t st = g_ctx.st;
+    if ((e = cudaMemcpyAsync(d_in, in, n_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return cuda_fail(e, "H2D copy");
+    int rc = snappy_b200_compress_device(d_in, n_bytes, mode, d_out, max_out, d_small, nullptr,
+                                         reinterpret_cast<uint32_t *>(d_small + 1), g_ctx.buf[2], g_ctx.cap[2], st);
+    if (rc != SNAPPY_B200_OK)
+        return rc;
+    if ((e = cudaMemcpyAsync(g_ctx.h_small, d_small, 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess)
+        return cuda_fail(e, "compress");
+    const uint64_t total = g_ctx.h_small[0];
+    const uint32_t status = (uint32_t)g_ctx.h_small[1];
+    if (status)
+        return status_to_error(status);
+    if (total > out_capacity)
+        return fail(SNAPPY_B200_ERR_CAPACITY, "compressed stream needs %llu bytes, capacity is %llu",
+                    (unsigned long long)total, (unsigned long long)out_capacity);
+    if ((e = cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess)
+        return cuda_fail(e, "D2H copy");
+    *out_bytes = total;
+    return SNAPPY_B200_OK;
+}
+
+int snappy_b200_uncompressed_length(const void *stream, uint64_t stream_bytes, uint64_t *n_bytes)
+{
+    if (!n_bytes)
+        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    *n_bytes = 0;
+    if (stream_bytes == 0)
+        return SNAPPY_B200_OK; // the reference's empty stream
+    if (!host_varint_decode(static_cast<const uint8_t *>(stream), stream_bytes, n_bytes))
+        return fail(SNAPPY_B200_ERR_CORRUPT, "bad varint preamble");
+    return SNAPPY_B200_OK;
+}
+
+int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void *out, uint64_t out_capacity,
+                                uint64_t *out_bytes)
+{
+    if (!out_bytes || (stream_bytes && !stream))
+        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    *out_bytes = 0;
+    if (stream_bytes == 0)
+        return SNAPPY_B200_OK;
+    uint64_t total = 0;
+    const unsigned hdr = host_varint_decode(static_cast<const uint8_t *>(stream), stream_bytes, &total);
+    if (!hdr)
+        return fail(SNAPPY_B200_ERR_CORRUPT, "bad varint preamble");
+    if (total > out_capacity)
+        return fail(SNAPPY_B200_ERR_CAPACITY, "output needs %llu bytes, capacity is %llu", (unsigned long long)total,
+                    (unsigned long long)out_capacity);
+    if (total == 0)
+        return stream_bytes == hdr ? SNAPPY_B200_OK : fail(SNAPPY_B200_ERR_CORRUPT, "trailing bytes after empty stream");
+    if (!out)
+        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    cudaError_t e = g_ctx.init();
+    if (e != cudaSuccess)
+        return cuda_fail(e, "context init");
+    const uint64_t nb = (total + kBlock - 1) / kBlock;
+    const size_t ws_bytes = index_workspace_bytes(stream_bytes);
+    if ((e = g_ctx.need(0, stream_bytes)) != cudaSuccess || (e = g_ctx.need(1, total)) != cudaSuccess ||
+        (e = g_ctx.need(2, ws_bytes)) != cudaSuccess || (e = g_ctx.need(3, (nb + 1) * 8 + 64)) != cudaSuccess)
+        return cuda_fail(e, "cudaMalloc");
+    uint8_t *d_stream = static_cast<uint8_t *>(g_ctx.buf[0]);
+    uint8_t *d_out = static_cast<uint8_t *>(g_ctx.buf[1]);
+    uint64_t *d_small = static_cast<uint64_t *>(g_ctx.buf[3]);
+    uint32_t *d_status = reinterpret_cast<uint32_t *>(d_small);
+    uint64_t *d_offsets = d_small + 2;
+    cudaStream_t st = g_ctx.st;
+    if ((e = cudaMemcpyAsync(d_stream, stream, stream_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemsetAsync(d_small, 0, 16, st)) != cudaSuccess)
+        return cuda_fail(e, "H2D copy");
+    int rc = snappy_b200_index_device(d_stream, stream_bytes, hdr, total, d_offsets, d_status, g_ctx.buf[2],
+                                      g_ctx.cap[2], st);
+    if (rc != SNAPPY_B200_OK)
+        return rc;
+    rc = snappy_b200_decompress_device_indexed(d_stream, d_offsets, nb, total, d_out, d_status, st);
+    if (rc != SNAPPY_B200_OK)
+        return rc;
+    if ((e = cudaMemcpyAsync(g_ctx.h_small, d_small, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess)
+        return cuda_fail(e, "decompress");
+    const uint32_t status = (uint32_t)g_ctx.h_small[0];
+    if (status)
+        return status_to_error(status);
+    if ((e = cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess)
+        return cuda_fail(e, "D2H copy");
+    *out_bytes = total;
+    return SNAPPY_B200_OK;
+}
+
+void snappy_b200_release(void)
+{
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    g_ctx.release();
+}
+
+} // extern "C"

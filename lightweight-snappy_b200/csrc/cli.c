@@ -1,0 +1,96 @@
+/* cli.c -- `snappy [-c|-b|-d] [-r] infile outfile`, the reference's command line
+ * (src/cmd.c:19-28, :56-105) in front of libsnappy_b200.so.  Same options and defaults;
+ * -r reports wall-clock time and throughput on the UNCOMPRESSED size for both directions
+ * (the reference used CPU time and the compressed size).                   */
+#define _POSIX_C_SOURCE 200809L
+#include <errno.h>
+#include <getopt.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "snappy_b200.h"
+#include "snappy_compression.h"
+#include "snappy_compression_tree.h"
+#include "snappy_decompression.h"
+
+static void usage(void)
+{
+    fprintf(stderr, "snappy [-c|-d|-b] [-r] [infile] [outfile]\n"
+                    "-c compress (hash table)\n"
+                    "-b compress (exact-key / BST match finder)\n"
+                    "-d decompress\n"
+                    "-r print sizes, ratio, time and throughput\n");
+    exit(EXIT_FAILURE);
+}
+
+static unsigned long long file_size(FILE *f)
+{
+    fseek(f, 0, SEEK_END);
+    unsigned long long s = (unsigned long long)ftell(f);
+    fseek(f, 0, SEEK_SET);
+    return s;
+}
+
+static double now(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+int main(int argc, char *argv[])
+{
+    enum { COMPRESS, COMPRESS_BST, UNCOMPRESS } mode = COMPRESS;
+    int report = 0, opt;
+    if (argc < 4)
+        usage();
+    while ((opt = getopt(argc, argv, "cbdr")) != -1) {
+        switch (opt) {
+        case 'c': mode = COMPRESS; break;
+        case 'b': mode = COMPRESS_BST; break;
+        case 'd': mode = UNCOMPRESS; break;
+        case 'r': report = 1; break;
+        default: usage();
+        }
+    }
+    const char *in_name = argv[argc - 2], *out_name = argv[argc - 1];
+    FILE *in = fopen(in_name, "rb");
+    if (!in) {
+        fprintf(stderr, "cannot open %s: %s\n", in_name, strerror(errno));
+        return EXIT_FAILURE;
+    }
+    FILE *out = fopen(out_name, "wb");
+    if (!out) {
+        fprintf(stderr, "cannot open %s: %s\n", out_name, strerror(errno));
+        fclose(in);
+        return EXIT_FAILURE;
+    }
+    const unsigned long long in_size = file_size(in);
+    int rc = 0;
+    const double t0 = now();
+    if (mode == COMPRESS)
+        snappy_compress(in, in_size, out);
+    else if (mode == COMPRESS_BST)
+        rc = snappy_compress_bst(in, in_size, out);
+    else
+        rc = snappy_decompress(in, out);
+    const double dt = now() - t0;
+    fclose(in);
+    fflush(out);
+    const unsigned long long out_size = (unsigned long long)ftell(out);
+    fclose(out);
+    if (rc != 0 || snappy_b200_last_error()[0]) {
+        fprintf(stderr, "snappy: failed: %s\n", snappy_b200_last_error());
+        return EXIT_FAILURE;
+    }
+    if (report) {
+        const unsigned long long unc = mode == UNCOMPRESS ? out_size : in_size;
+        const unsigned long long cmp = mode == UNCOMPRESS ? in_size : out_size;
+        printf("uncompressed = %llu bytes\ncompressed   = %llu bytes\nratio        = %.3f\n", unc, cmp,
+               cmp ? (double)unc / (double)cmp : 0.0);
+        printf("time         = %.6f s (wall)\nthroughput   = %.1f MB/s (uncompressed)\n", dt, dt > 0 ? unc / dt / 1e6 : 0.0);
+    }
+    return EXIT_SUCCESS;
+}

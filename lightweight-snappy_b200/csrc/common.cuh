@@ -1,0 +1,73 @@
+// common.cuh -- device helpers shared by the codec kernels (sm_100a).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "snappy_b200.h"
+
+namespace sb200 {
+
+constexpr uint32_t kBlock = SNAPPY_B200_BLOCK_SIZE;
+constexpr uint32_t kSlot = SNAPPY_B200_SLOT_STRIDE;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kHashMul = 0x1e35a7bdu;  // reference: src/snappy_compression.c:82
+constexpr uint32_t kAbortMark = 0xffffffffu; // sizes[] entry of a block a table tier gave up on
+
+// ---- read-only input access -------------------------------------------------------------
+// `base` is 4-byte aligned.  Word `last_word` is the last one that holds a valid byte, so the
+// second load is clamped instead of running past the buffer when pos is word aligned.
+__device__ __forceinline__ uint32_t ld_le32(const uint8_t *__restrict__ base, uint32_t pos, uint32_t last_word)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(base);
+    const uint32_t i = pos >> 2;
+    const uint32_t lo = __ldg(w + i);
+    const uint32_t hi = __ldg(w + min(i + 1, last_word));
+    return __funnelshift_r(lo, hi, (pos & 3u) * 8u);
+}
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// Big-endian 4-byte load: reference get_next_u32, src/snappy_compression.c:239-241.
+__device__ __forceinline__ uint32_t ld_be32(const uint8_t *__restrict__ base, uint32_t pos, uint32_t last_word)
+{
+    return bswap32(ld_le32(base, pos, last_word));
+}
+
+// ---- cooperative byte copy, global -> global, any alignment -------------------------------
+// `nt` threads (ids 0..nt-1) copy len bytes.  src is read through the read-only path, so it
+// must not alias anything written by this kernel.  Large copies go in 16-byte destination
+// chunks; the source words are funnel-shifted to the destination alignment.
+__device__ __forceinline__ void coop_copy_ro(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint32_t len,
+                                             uint32_t tid, uint32_t nt)
+{
+    if (len < 64) {
+        for (uint32_t i = tid; i < len; i += nt)
+            dst[i] = __ldg(src + i);
+        return;
+    }
+    const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+    if (tid < head)
+        dst[tid] = __ldg(src + tid);
+    const uint32_t nchunk = (len - head) >> 4;
+    const uint8_t *s0 = src + head;
+    const uint32_t sa = (uint32_t)(reinterpret_cast<uintptr_t>(s0) & 3u);
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s0 - sa);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+    const uint32_t sh = sa * 8u;
+    const uint32_t w4i = sa ? 4u : 3u; // the fifth word is only touched when it holds wanted bytes
+    for (uint32_t c = tid; c < nchunk; c += nt) {
+        const uint32_t *p = sw + 4u * c;
+        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + w4i);
+        uint4 v;
+        v.x = __funnelshift_r(w0, w1, sh);
+        v.y = __funnelshift_r(w1, w2, sh);
+        v.z = __funnelshift_r(w2, w3, sh);
+        v.w = __funnelshift_r(w3, w4, sh);
+        d4[c] = v;
+    }
+    for (uint32_t i = head + (nchunk << 4) + tid; i < len; i += nt)
+        dst[i] = __ldg(src + i);
+}
+
+} // namespace sb200

@@ -1,0 +1,154 @@
+// dropin.cpp -- the reference's own entry points (include/snappy_compression.h,
+// snappy_compression_tree.h, snappy_decompression.h, varint.h, buffer_compression.h) on top
+// of the host-buffer API.  Same symbol names, signatures, FILE* ownership rules and stream
+// bytes as the reference; the work happens on the GPU.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "buffer_compression.h"
+#include "snappy_b200.h"
+#include "snappy_compression.h"
+#include "snappy_compression_tree.h"
+#include "snappy_decompression.h"
+#include "varint.h"
+
+namespace {
+
+// Reads from the current position to EOF (the reference's fread loop, src/snappy_compression.c:210-213).
+bool read_all(FILE *f, uint64_t hint, std::vector<uint8_t> &buf)
+{
+    buf.clear();
+    size_t cap = hint ? hint + 1 : (1u << 16);
+    size_t n = 0;
+    for (;;) {
+        buf.resize(cap);
+        const size_t got = fread(buf.data() + n, 1, cap - n, f);
+        n += got;
+        if (n < cap) {
+            if (ferror(f))
+                return false;
+            break;
+        }
+        cap *= 2;
+    }
+    buf.resize(n);
+    return true;
+}
+
+int compress_file(FILE *in, unsigned long long declared, FILE *out, int mode)
+{
+    std::vector<uint8_t> data;
+    if (!in || !out || !read_all(in, declared, data))
+        return SNAPPY_B200_ERR_IO;
+    if (data.empty())
+        return SNAPPY_B200_OK; // reference: empty input -> empty output
+    std::vector<uint8_t> stream(snappy_b200_max_compressed_bytes(data.size()));
+    uint64_t n = 0;
+    const int rc = snappy_b200_compress_host(data.data(), data.size(), mode, stream.data(), stream.size(), &n);
+    if (rc != SNAPPY_B200_OK) {
+        fprintf(stderr, "snappy_b200: %s\n", snappy_b200_last_error());
+        return rc;
+    }
+    // The reference writes the DECLARED size into the preamble (src/snappy_compression.c:417)
+    // and then whatever the file really held; keep that even when the two disagree.
+    unsigned char hdr[10];
+    const unsigned hdr_real = parse_to_varint(data.size(), hdr);
+    const unsigned hdr_decl = parse_to_varint(declared, hdr);
+    if (fwrite(hdr, 1, hdr_decl, out) != hdr_decl)
+        return SNAPPY_B200_ERR_IO;
+    if (fwrite(stream.data() + hdr_real, 1, n - hdr_real, out) != n - hdr_real)
+        return SNAPPY_B200_ERR_IO;
+    return SNAPPY_B200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+void snappy_compress(FILE *file_input, unsigned long long input_size, FILE *file_compressed)
+{
+    (void)compress_file(file_input, input_size, file_compressed, SNAPPY_B200_MODE_HASH);
+}
+
+int snappy_compress_bst(FILE *file_input, unsigned long long input_size, FILE *file_compressed)
+{
+    return compress_file(file_input, input_size, file_compressed, SNAPPY_B200_MODE_BST);
+}
+
+int snappy_decompress(FILE *file_input, FILE *file_decompressed)
+{
+    std::vector<uint8_t> stream;
+    if (!file_input || !file_decompressed || !read_all(file_input, 0, stream))
+        return SNAPPY_B200_ERR_IO;
+    uint64_t total = 0;
+    int rc = snappy_b200_uncompressed_length(stream.data(), stream.size(), &total);
+    if (rc == SNAPPY_B200_OK && total) {
+        std::vector<uint8_t> out(total);
+        uint64_t n = 0;
+        rc = snappy_b200_decompress_host(stream.data(), stream.size(), out.data(), out.size(), &n);
+        if (rc == SNAPPY_B200_OK && fwrite(out.data(), 1, n, file_decompressed) != n)
+            rc = SNAPPY_B200_ERR_IO;
+    }
+    if (rc != SNAPPY_B200_OK && rc != SNAPPY_B200_ERR_IO)
+        fprintf(stderr, "snappy_b200: %s\n", snappy_b200_last_error());
+    return rc;
+}
+
+// ---- varint.h (reference src/varint.c) ---------------------------------------------------
+unsigned int parse_to_varint(unsigned long long n, unsigned char *varint)
+{
+    unsigned int k = 0;
+    while (n >= 0x80u) {
+        varint[k++] = (unsigned char)(n | 0x80u);
+        n >>= 7;
+    }
+    varint[k++] = (unsigned char)n;
+    return k;
+}
+
+int str_varint_to_dim_(unsigned char *varint)
+{
+    // the reference accumulates in an int (src/varint.c:44-58): keep its wrap-around
+    unsigned int result = 0, mult = 1;
+    unsigned char b;
+    do {
+        b = *varint++;
+        result += (unsigned int)(b & 0x7fu) * mult;
+        mult *= 128u;
+    } while (b & 0x80u);
+    return (int)result;
+}
+
+int varint_to_dim(FILE *source)
+{
+    unsigned int result = 0, mult = 1;
+    unsigned char b = 0;
+    do {
+        if (fread(&b, 1, 1, source) != 1)
+            break;
+        result += (unsigned int)(b & 0x7fu) * mult;
+        mult *= 128u;
+    } while (b & 0x80u);
+    return (int)result;
+}
+
+// ---- buffer_compression.h (reference src/buffer_compression.c) ----------------------------
+void init_Buffer(Buffer *bf, unsigned int buffer_size)
+{
+    bf->current = (char *)calloc(buffer_size, 1);
+    bf->beginning = bf->current;
+    bf->bytes_left = buffer_size;
+}
+
+void move_current(Buffer *bf, unsigned int offset)
+{
+    bf->current += offset;
+    bf->bytes_left -= offset;
+}
+
+void reset(Buffer *bf) { bf->current = bf->beginning; }
+
+} // extern "C"

@@ -1,0 +1,406 @@
+// index.cu -- K0: where does every 64 KiB output block start inside an index-less stream?
+//
+// The reference discovers this implicitly by walking the elements one after another
+// (src/snappy_decompression.c:353-356): block boundaries are not recorded in the format
+// (src/snappy_compression.c:334-336 just appends blocks).  A sequential tag walk over a
+// gigabyte is hopeless on a GPU, so the walk is made parallel by speculation:
+//
+//   A  k_index_spec    the stream body is cut into 128-byte segments, one thread each.  Every
+//                      thread walks elements from the first byte of its segment as if an
+//                      element started there, remembers the visited offsets in a 128-bit map
+//                      and the offset at which it leaves the segment.  Snappy streams
+//                      re-synchronise within a few elements, so most of these walks merge
+//                      into the true element chain long before the segment ends.
+//   B  k_index_scatter / k_index_apply   relaxation rounds.  Every segment that currently
+//                      believes it holds an element start publishes its exit to the segment
+//                      it lands in (and marks the segments a long literal jumps over as
+//                      holding none); when several segments disagree the lowest source wins.
+//                      A segment whose entry changed re-walks from the new entry until it
+//                      meets its old path.  Segment 0's entry is known, so the beliefs are
+//                      correct on a prefix that grows every round; a round that changes
+//                      nothing is the unique fixed point = the true chain.  Typical streams
+//                      need 2-3 rounds; an adversarial one degrades to sequential but stays
+//                      correct.
+//   C  k_index_outlen  every live segment sums the output bytes of its elements
+//      k_scan_u64      exclusive scan -> output offset of every segment
+//   D  k_index_blocks  every live segment walks once more and records the stream offset of
+//                      each element that starts a 64 KiB output block; elements that straddle
+//                      a block boundary (legal raw Snappy, never produced by this framing) are
+//                      reported as SNAPPY_B200_ST_FRAMING.
+#include "common.cuh"
+
+namespace sb200 {
+
+constexpr uint32_t kSeg = 128;          // bytes of stream per segment
+constexpr uint32_t kNoEntry = 0xffu;    // E[t]: the segment holds no element start
+constexpr unsigned long long kNone = ~0ull;
+
+struct Elem {
+    uint64_t size; // bytes of stream this element occupies (header + literal payload)
+    uint64_t out;  // bytes of output it produces
+    bool ok;       // header fits in the body
+};
+
+// Decodes the element header at body offset e (reference: decompressor :290-333, do_literal
+// :193-224).  Bytes past the end of the body read as zero and clear `ok`.
+__device__ __forceinline__ Elem decode_at(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t e)
+{
+    Elem r;
+    const uint32_t tag = __ldg(body + e);
+    const uint32_t type = tag & 3u;
+    uint32_t extra; // header bytes after the tag
+    if (type == 0) {
+        const uint32_t m = tag >> 2;
+        extra = m >= 60 ? m - 59 : 0;
+    } else {
+        extra = type == 1 ? 1 : (type == 2 ? 2 : 4);
+    }
+    r.ok = e + 1 + extra <= body_len;
+    uint32_t raw = 0;
+    if (type == 0 && extra && r.ok) {
+        for (uint32_t k = 0; k < extra; ++k)
+            raw |= (uint32_t)__ldg(body + e + 1 + k) << (8 * k);
+    }
+    if (type == 0) {
+        const uint64_t len = (uint64_t)((tag >> 2) >= 60 ? raw : (tag >> 2)) + 1;
+        r.size = 1 + extra + len;
+        r.out = len;
+    } else {
+        r.size = 1 + extra;
+        r.out = type == 1 ? ((tag >> 2) & 7u) + 4 : (tag >> 2) + 1;
+    }
+    return r;
+}
+
+struct Path {
+    uint32_t bits[4];
+    __device__ __forceinline__ void clear() { bits[0] = bits[1] = bits[2] = bits[3] = 0; }
+    __device__ __forceinline__ void set(uint32_t i)
+    {
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+            if ((i >> 5) == (uint32_t)w)
+                bits[w] |= 1u << (i & 31);
+    }
+    __device__ __forceinline__ bool test(uint32_t i) const
+    {
+        uint32_t v = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+            if ((i >> 5) == (uint32_t)w)
+                v = bits[w];
+        return (v >> (i & 31)) & 1u;
+    }
+};
+
+// Walks from e until the segment [seg_lo, seg_hi) is left, or (when `old` is given) until an
+// offset already on the old path is met.  Visited offsets are recorded in `fresh`.
+__device__ __forceinline__ uint64_t walk(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t seg_lo,
+                                         uint64_t seg_hi, uint64_t e, const Path *old, Path &fresh, bool &merged)
+{
+    merged = false;
+    while (e < seg_hi) {
+        const uint32_t rel = (uint32_t)(e - seg_lo);
+        if (old && old->test(rel)) {
+            merged = true;
+            return e;
+        }
+        fresh.set(rel);
+        const Elem el = decode_at(body, body_len, e);
+        e += el.size; // seg_hi <= body_len, sizes < 2^33: no overflow
+    }
+    return e;
+}
+
+__global__ void __launch_bounds__(256) k_index_spec(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
+                                                    uint4 *__restrict__ paths, uint64_t *__restrict__ exits,
+                                                    uint8_t *__restrict__ entry)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= nseg)
+        return;
+    const uint64_t lo = t * kSeg;
+    const uint64_t hi = min(lo + kSeg, body_len);
+    Path p;
+    p.clear();
+    bool merged;
+    const uint64_t x = walk(body, body_len, lo, hi, lo, nullptr, p, merged);
+    paths[t] = make_uint4(p.bits[0], p.bits[1], p.bits[2], p.bits[3]);
+    exits[t] = x;
+    entry[t] = 0; // everybody starts out believing an element begins at its first byte
+}
+
+__global__ void __launch_bounds__(256) k_index_scatter(uint64_t body_len, uint64_t nseg,
+                                                       const uint64_t *__restrict__ exits,
+                                                       const uint8_t *__restrict__ entry,
+                                                       unsigned long long *__restrict__ claim)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= nseg || entry[t] == kNoEntry)
+        return;
+    const uint64_t x = exits[t];
+    const uint64_t u = x / kSeg; // segment the chain lands in
+    // Segments jumped over hold no element start.  An element of this framing never spans more
+    // than one 64 KiB block (+ header), which bounds the work a mis-speculated "huge literal"
+    // can cause; a true element that long is reported as SNAPPY_B200_ST_FRAMING by k_index_outlen.
+    const uint64_t vmax = min(min(u, nseg), t + 1 + (kBlock + 1024) / kSeg);
+    for (uint64_t v = t + 1; v < vmax; ++v)
+        atomicMin(claim + v, (unsigned long long)((t << 8) | kNoEntry));
+    if (u < nseg && x < body_len)
+        atomicMin(claim + u, (unsigned long long)((t << 8) | (x - u * kSeg)));
+}
+
+__global__ void __launch_bounds__(256) k_index_apply(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
+                                                     uint4 *__restrict__ paths, uint64_t *__restrict__ exits,
+                                                     uint8_t *__restrict__ entry,
+                                                     unsigned long long *__restrict__ claim,
+                                                     uint32_t *__restrict__ changed)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= nseg)
+        return;
+    const unsigned long long c = claim[t];
+    claim[t] = kNone; // ready for the next round
+    const uint32_t ne = t == 0 ? 0u : (c == kNone ? kNoEntry : (uint32_t)(c & 0xffu));
+    const uint32_t old = entry[t];
+    if (ne == old)
+        return;
+    entry[t] = (uint8_t)ne;
+    atomicOr(changed, 1u);
+    if (ne == kNoEntry)
+        return;
+    const uint64_t lo = t * kSeg;
+    const uint64_t hi = min(lo + kSeg, body_len);
+    const uint4 pv = paths[t];
+    Path p;
+    p.bits[0] = pv.x, p.bits[1] = pv.y, p.bits[2] = pv.z, p.bits[3] = pv.w;
+    Path fresh;
+    fresh.clear();
+    bool merged;
+    const uint64_t x = walk(body, body_len, lo, hi, lo + ne, &p, fresh, merged);
+    if (merged) {
+        // rejoined the old path: the old exit stands, and every offset of either walk leads to it
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+            fresh.bits[w] |= p.bits[w];
+    } else {
+        exits[t] = x; // a different chain: only its own offsets are known to lead to x
+    }
+    paths[t] = make_uint4(fresh.bits[0], fresh.bits[1], fresh.bits[2], fresh.bits[3]);
+}
+
+// C: output bytes produced by the elements that start in each live segment.
+__global__ void __launch_bounds__(256) k_index_outlen(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
+                                                      const uint8_t *__restrict__ entry, uint64_t *__restrict__ outlen,
+                                                      uint32_t *__restrict__ status)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= nseg)
+        return;
+    uint64_t sum = 0;
+    const uint32_t en = entry[t];
+    if (en != kNoEntry) {
+        const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
+        uint64_t e = lo + en;
+        while (e < hi) {
+            const Elem el = decode_at(body, body_len, e);
+            if (!el.ok || e + el.size > body_len) {
+                atomicOr(status, SNAPPY_B200_ST_CORRUPT);
+                break;
+            }
+            if (el.out > kBlock)
+                atomicOr(status, SNAPPY_B200_ST_FRAMING);
+            sum += el.out;
+            e += el.size;
+        }
+    }
+    outlen[t] = sum;
+}
+
+// Exclusive scan of a u64 array by one CTA (the array has one entry per 128 stream bytes).
+__global__ void __launch_bounds__(1024) k_scan_u64(const uint64_t *__restrict__ in, uint64_t n,
+                                                   uint64_t *__restrict__ out, uint64_t *__restrict__ total)
+{
+    constexpr int kItems = 8;
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t carry_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0)
+        carry_s = 0;
+    __syncthreads();
+    for (uint64_t start = 0; start < n; start += 1024ull * kItems) {
+        uint64_t v[kItems], sum = 0;
+        const uint64_t i0 = start + (uint64_t)tid * kItems;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            v[k] = i0 + k < n ? in[i0 + k] : 0;
+            sum += v[k];
+        }
+        uint64_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t s = __shfl_up_sync(kFull, incl, d);
+            if ((int)lane >= d)
+                incl += s;
+        }
+        if (lane == 31)
+            warp_sum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const uint64_t w = warp_sum[lane];
+            uint64_t wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t s = __shfl_up_sync(kFull, wi, d);
+                if ((int)lane >= d)
+                    wi += s;
+            }
+            warp_sum[lane] = wi - w;
+        }
+        __syncthreads();
+        uint64_t run = carry_s + warp_sum[wid] + (incl - sum);
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            if (i0 + k < n)
+                out[i0 + k] = run;
+            run += v[k];
+        }
+        __syncthreads();
+        if (tid == 1023)
+            carry_s = run;
+        __syncthreads();
+    }
+    if (tid == 0)
+        *total = carry_s;
+}
+
+// D: stream offset of the element that opens each 64 KiB output block.
+__global__ void __launch_bounds__(256) k_index_blocks(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
+                                                      const uint8_t *__restrict__ entry,
+                                                      const uint64_t *__restrict__ outoff, uint64_t body_offset,
+                                                      uint64_t n_blocks, uint64_t *__restrict__ block_offsets,
+                                                      uint32_t *__restrict__ status)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= nseg)
+        return;
+    const uint32_t en = entry[t];
+    if (en == kNoEntry)
+        return;
+    const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
+    uint64_t e = lo + en, op = outoff[t];
+    while (e < hi) {
+        const Elem el = decode_at(body, body_len, e);
+        if (!el.ok || e + el.size > body_len)
+            break; // already flagged by k_index_outlen
+        const uint64_t within = op & (kBlock - 1);
+        if (within == 0) {
+            const uint64_t bi = op / kBlock;
+            if (bi < n_blocks)
+                block_offsets[bi] = body_offset + e;
+        }
+        if (within + el.out > kBlock)
+            atomicOr(status, SNAPPY_B200_ST_FRAMING);
+        op += el.out;
+        e += el.size;
+    }
+}
+
+__global__ void k_index_finish(const uint64_t *__restrict__ total, uint64_t total_out, uint64_t stream_bytes,
+                               uint64_t n_blocks, uint64_t *__restrict__ block_offsets, uint32_t *__restrict__ status)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        block_offsets[n_blocks] = stream_bytes;
+        if (*total != total_out)
+            atomicOr(status, SNAPPY_B200_ST_CORRUPT);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n)
+        p[i] = v;
+}
+
+// ------------------------------------------------------------------------------- host side
+struct IndexWorkspace {
+    uint4 *paths;
+    uint64_t *exits;
+    unsigned long long *claim;
+    uint64_t *outlen;
+    uint64_t *outoff;
+    uint64_t *total;
+    uint32_t *changed;
+    uint8_t *entry;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t index_workspace_bytes(uint64_t stream_bytes)
+{
+    const uint64_t nseg = (stream_bytes + kSeg - 1) / kSeg + 1;
+    return align_up(nseg * 16, 256) + 4 * align_up(nseg * 8, 256) + 256 + 256 + align_up(nseg, 256) + 256;
+}
+
+static IndexWorkspace carve(void *ws, uint64_t stream_bytes)
+{
+    const uint64_t nseg = (stream_bytes + kSeg - 1) / kSeg + 1;
+    uint8_t *p = static_cast<uint8_t *>(ws);
+    IndexWorkspace w;
+    w.paths = reinterpret_cast<uint4 *>(p), p += align_up(nseg * 16, 256);
+    w.exits = reinterpret_cast<uint64_t *>(p), p += align_up(nseg * 8, 256);
+    w.claim = reinterpret_cast<unsigned long long *>(p), p += align_up(nseg * 8, 256);
+    w.outlen = reinterpret_cast<uint64_t *>(p), p += align_up(nseg * 8, 256);
+    w.outoff = reinterpret_cast<uint64_t *>(p), p += align_up(nseg * 8, 256);
+    w.total = reinterpret_cast<uint64_t *>(p), p += 256;
+    w.changed = reinterpret_cast<uint32_t *>(p), p += 256;
+    w.entry = p;
+    return w;
+}
+
+// Synchronises the stream between relaxation rounds (it has to read the "changed" flag).
+cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset, uint64_t total_out,
+                      uint64_t *d_block_offsets, uint32_t *d_status, void *d_ws, cudaStream_t st, uint64_t *launches)
+{
+    const uint64_t n_blocks = (total_out + kBlock - 1) / kBlock;
+    const uint64_t body_len = stream_bytes - body_offset;
+    const uint8_t *body = d_stream + body_offset;
+    const uint64_t nseg = (body_len + kSeg - 1) / kSeg;
+    IndexWorkspace w = carve(d_ws, stream_bytes);
+    cudaError_t e;
+    if (nseg == 0) {
+        k_index_finish<<<1, 32, 0, st>>>(w.total, total_out, stream_bytes, n_blocks, d_block_offsets, d_status);
+        *launches += 1;
+        // total is uninitialised here; an empty body is only legal for total_out == 0
+        return cudaGetLastError();
+    }
+    const unsigned grid = (unsigned)((nseg + 255) / 256);
+    k_fill_u64<<<grid, 256, 0, st>>>(w.claim, nseg, kNone);
+    k_index_spec<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits, w.entry);
+    *launches += 2;
+    const uint64_t max_rounds = nseg + 2;
+    for (uint64_t round = 0; round < max_rounds; ++round) {
+        if ((e = cudaMemsetAsync(w.changed, 0, 4, st)) != cudaSuccess)
+            return e;
+        k_index_scatter<<<grid, 256, 0, st>>>(body_len, nseg, w.exits, w.entry, w.claim);
+        k_index_apply<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits, w.entry, w.claim, w.changed);
+        *launches += 2;
+        uint32_t changed = 0;
+        if ((e = cudaMemcpyAsync(&changed, w.changed, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            return e;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess)
+            return e;
+        if (!changed)
+            break;
+    }
+    k_index_outlen<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outlen, d_status);
+    k_scan_u64<<<1, 1024, 0, st>>>(w.outlen, nseg, w.outoff, w.total);
+    k_index_blocks<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outoff, body_offset, n_blocks,
+                                         d_block_offsets, d_status);
+    k_index_finish<<<1, 32, 0, st>>>(w.total, total_out, stream_bytes, n_blocks, d_block_offsets, d_status);
+    *launches += 4;
+    return cudaGetLastError();
+}
+
+} // namespace sb200

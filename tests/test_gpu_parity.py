@@ -1,0 +1,174 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the
+C-ABI, against the CPU oracle and the golden vectors captured from the reference."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import datasets
+from lightweight_snappy_b200 import api, corpus
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _first_diff(a, b):
+    n = min(a.size, b.size)
+    d = np.nonzero(a[:n] != b[:n])[0]
+    return int(d[0]) if d.size else n
+
+
+def _assert_same(got, want, what):
+    if got.size != want.size or not np.array_equal(got, want):
+        i = _first_diff(got, want)
+        raise AssertionError(f"{what}: sizes {got.size} vs {want.size}, first difference at byte {i} "
+                             f"(block {i // 65536}): got {got[i:i + 16].tobytes().hex()} want {want[i:i + 16].tobytes().hex()}")
+
+
+@pytest.mark.parametrize("case", GOLDEN["cases"], ids=lambda c: c["spec"])
+def test_golden_vectors(case):
+    data = datasets.gen(case["spec"])
+    assert _sha(data) == case["input_sha256"]
+    for name, fn in (("hash", api.snappy_compress), ("bst", api.snappy_compress_bst)):
+        s = fn(data)
+        assert s.size == case[name]["len"], (name, s.size, case[name]["len"])
+        assert _sha(s) == case[name]["sha256"], name
+        _assert_same(api.snappy_decompress(s), data, f"roundtrip {name}")
+
+
+def _fuzz_specs():
+    specs = []
+    for n in datasets.boundary_sizes():
+        specs += [f"corpus:text:2:{n % 1000}:{n}", f"sym:5:{n}:{n}", f"lz:{n}:{n}", f"corpus:lowent:5:{n % 777}:{n}"]
+    specs += [f"period:{p}:{p}:{n}" for p in (1, 2, 3, 5, 64, 65, 2047, 2048, 2049) for n in (4100, 66000)]
+    specs += [f"corpus:random:7:0:{n}" for n in (1, 100, 65536, 65537, 140000)]
+    specs += [f"sym:{k}:{k}:{70000}" for k in (1, 2, 4, 16, 64, 200)]
+    return specs
+
+
+def test_fuzz_against_oracle(oracle):
+    for spec in _fuzz_specs():
+        data = datasets.gen(spec)
+        for mode, fn in ((0, api.snappy_compress), (1, api.snappy_compress_bst)):
+            want = oracle.compress(data, mode)
+            _assert_same(fn(data), want, f"{spec} mode {mode}")
+        _assert_same(api.snappy_decompress(oracle.compress(data, 0)), data, f"{spec} decode(hash stream)")
+        _assert_same(api.snappy_decompress(oracle.compress(data, 1)), data, f"{spec} decode(bst stream)")
+
+
+def test_empty_input():
+    assert api.snappy_compress(np.zeros(0, np.uint8)).size == 0
+    assert api.snappy_compress_bst(np.zeros(0, np.uint8)).size == 0
+    assert api.snappy_decompress(np.zeros(0, np.uint8)).size == 0
+
+
+@pytest.mark.parametrize("kind", ["mixed", "text", "lowent", "random", "lowent_random"])
+def test_device_api_64mib_against_oracle(oracle, kind):
+    import torch
+    n = 64 << 20 if kind in ("mixed", "lowent_random") else 16 << 20
+    data = corpus.make_corpus(kind, n, device="cuda")
+    host = data.cpu().numpy()
+    codec = api.DeviceCodec(n)
+    for mode in (0, 1):
+        if mode == 1 and kind in ("text", "mixed") and n > (16 << 20):
+            host_m, data_m = host[: 16 << 20], data[: 16 << 20]  # the BST oracle is slow on text
+        else:
+            host_m, data_m = host, data
+        want, sizes = oracle.compress(host_m, mode, with_sizes=True)
+        codec.compress(data_m, mode)
+        got = codec.result_stream().cpu().numpy()
+        _assert_same(got, want, f"{kind} mode {mode} stream")
+        nb = api.block_count(host_m.size)
+        offs = codec.block_offsets[: nb + 1].cpu().numpy()
+        assert np.array_equal(np.diff(offs).astype(np.uint32), sizes), "side index"
+        # decode with the side index ...
+        out = torch.empty(host_m.size, dtype=torch.uint8, device="cuda")
+        codec.decompress_indexed(codec.stream_buf, codec.block_offsets, host_m.size, out)
+        codec.check_status()
+        assert torch.equal(out, data_m)
+        # ... and with the index rebuilt from the bare stream (K0)
+        hdr = len(oracle.varint_encode(host_m.size))
+        offs2 = torch.zeros(nb + 1, dtype=torch.int64, device="cuda")
+        codec.index(codec.stream_buf, got.size, hdr, host_m.size, offs2)
+        codec.check_status()
+        assert np.array_equal(offs2.cpu().numpy(), offs), "K0 block offsets"
+        want_offs, _ = oracle.block_index(want)
+        assert np.array_equal(offs.astype(np.uint64), want_offs)
+
+
+def test_decoder_foreign_and_malformed_streams(oracle):
+    # copy-4 elements (src/snappy_decompression.c:323-327) never come out of the compressors
+    stream = b"\x08" + b"\x0cabcd" + bytes([(3 << 2) | 3, 4, 0, 0, 0])
+    assert api.snappy_decompress(np.frombuffer(stream, np.uint8)).tobytes() == b"abcdabcd"
+    # slide example: literal of 67 then copy-1 len 6 offset 63
+    lit = bytes(range(67))
+    stream = b"\x49" + b"\xf0\x42" + lit + b"\x09\x3f"
+    assert api.snappy_decompress(np.frombuffer(stream, np.uint8)).tobytes() == lit + lit[4:10]
+    for bad in (b"\x08\x0cabcd" + bytes([(3 << 2) | 2, 9, 0]),   # offset beyond the output
+                b"\x08\x0cab",                                    # truncated literal
+                b"\x08\x0cabcd\x0cabcd",                          # more output than declared
+                b"\x20\x0cabcd"):                                 # less output than declared
+        with pytest.raises(api.SnappyError):
+            api.snappy_decompress(np.frombuffer(bad, np.uint8))
+
+
+def test_decode_google_snappy_streams():
+    pa = pytest.importorskip("pyarrow")
+    codec = pa.Codec("snappy")
+    for spec in ("corpus:text:0:0:300000", "corpus:lowent:1:0:200000", "corpus:random:2:0:70000", "rep:0:200000",
+                 "lz:9:150000"):
+        data = datasets.gen(spec)
+        foreign = np.frombuffer(codec.compress(data.tobytes()).to_pybytes(), np.uint8)
+        _assert_same(api.snappy_decompress(foreign), data, f"google stream of {spec}")
+        # and Google's decoder accepts ours
+        mine = api.snappy_compress(data)
+        back = codec.decompress(mine.tobytes(), decompressed_size=data.size).to_pybytes()
+        assert back == data.tobytes()
+
+
+def test_roundtrip_properties_at_scale():
+    """Size-independent properties at a size the oracle is too slow for: round trip,
+    determinism, and block independence (a block's bytes do not depend on its neighbours)."""
+    import torch
+    n = 256 << 20
+    data = corpus.make_corpus("mixed", n, device="cuda")
+    codec = api.DeviceCodec(n)
+    codec.compress(data, 0)
+    s1 = codec.result_stream().clone()
+    offs1 = codec.block_offsets.clone()
+    out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    codec.decompress_indexed(s1, offs1, n, out)
+    codec.check_status()
+    assert torch.equal(out, data)
+    codec.compress(data, 0)
+    assert torch.equal(codec.result_stream(), s1), "compression is deterministic"
+    # block independence: compress the second half alone, compare block bodies
+    half = n // 2
+    codec.compress(data[half:], 0)
+    s2 = codec.result_stream().clone()
+    offs2 = codec.block_offsets[: half // 65536 + 1].clone()
+    b1 = s1[int(offs1[half // 65536]):]
+    b2 = s2[int(offs2[0]):]
+    assert torch.equal(b1, b2)
+    ratio = n / s1.numel()
+    assert 1.5 < ratio < 4.0, ratio
+
+
+def test_cli_roundtrip(tmp_path, oracle):
+    import subprocess
+    data = datasets.gen("corpus:mixed:0:900000:400000")
+    src, snp, bsn, dec = (tmp_path / x for x in ("in.bin", "out.snp", "out.bsnp", "out.dec"))
+    src.write_bytes(data.tobytes())
+    subprocess.run([api.CLI_PATH, "-c", str(src), str(snp)], check=True)
+    subprocess.run([api.CLI_PATH, "-b", "-r", str(src), str(bsn)], check=True)
+    subprocess.run([api.CLI_PATH, "-d", str(snp), str(dec)], check=True)
+    assert snp.read_bytes() == oracle.compress(data, 0).tobytes()
+    assert bsn.read_bytes() == oracle.compress(data, 1).tobytes()
+    assert dec.read_bytes() == data.tobytes()
