@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Snappy hot path on B200 (BASELINE.json configs[1] and [2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one pass of the hot path over one batch: the 1 GiB synthetic *mixed* corpus
+(text-like / low-entropy / random in 1 MiB segments) per GPU.
+
+  value            decompression of the index-less reference-format stream, device resident:
+                   uncompressed bytes of all ranks / max-over-ranks CUDA-event time of K steps
+                   (each step = K0 boundary discovery + block decode)
+  compress{}       the same for hash-table compression (configs[2]), timed in the same run
+  e2e              the same metric through the host-buffer C-ABI call (pinned host buffers,
+                   H2D + D2H inside the timed region)
+  roofline         dominant kernel (block decode): (C + U) / its own CUDA-event time vs the
+                   measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline     the reference's CPU decoder (oracle/_ref when built, else the oracle port)
+                   on a bounded sample of the same corpus, one process per host core
+
+Multi-GPU: one process per GPU under torchrun, blocks partitioned by rank (each rank owns its
+own 1 GiB of corpus: weak scaling), no collective on the data path; NCCL only carries the
+barrier and the max-over-ranks of the timings.
+
+`--impl reference` times the reference's own CPU implementation (all host cores) on a bounded
+sample of the same workload and prints the same JSON line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GIB = 1 << 30
+SEED = 20261018
+METRIC = "decompress GB/s (uncompressed)"
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def _cpu_worker(args):
+    """One host core: generate a shard of the mixed corpus, then time the CPU codec on it."""
+    shard, n_bytes, use_ref = args
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    from lightweight_snappy_b200 import corpus
+    import oracle_lib
+    data = corpus.make_corpus("mixed", n_bytes, seed=SEED, first_segment=shard * (n_bytes >> 20)).numpy()
+    codec = oracle_lib.Reference() if use_ref else oracle_lib.Oracle()
+    t0 = time.perf_counter()
+    stream = codec.compress(data, 0)
+    t1 = time.perf_counter()
+    back = codec.decompress(stream, data.size)
+    t2 = time.perf_counter()
+    ok = bool(back.size == data.size and np.array_equal(back, data))
+    return {"n": int(data.size), "c": int(stream.size), "t_comp": t1 - t0, "t_decomp": t2 - t1, "ok": ok}
+
+
+def cpu_baseline(sample_mib_per_core: int = 48, cores: int | None = None) -> dict:
+    """Reference CPU codec, one process per host core, each on its own shard."""
+    import multiprocessing as mp
+    import oracle_lib
+    if not os.path.exists(oracle_lib.ORACLE_SO):
+        oracle_lib.build(ref=False)
+    use_ref = oracle_lib.Reference.available()
+    cores = cores or os.cpu_count() or 1
+    n = sample_mib_per_core << 20
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(i, n, use_ref) for i in range(cores)])
+    total = sum(r["n"] for r in res)
+    t_d = max(r["t_decomp"] for r in res)
+    t_c = max(r["t_comp"] for r in res)
+    return {
+        "value": total / t_d / 1e9, "unit": "GB/s", "cores": cores, "kind": "reference" if use_ref else "port",
+        "sample": f"{cores} x {sample_mib_per_core} MiB shards of the mixed corpus, one process per core, "
+                  f"aggregate = total bytes / slowest process",
+        "compress_value": total / t_c / 1e9,
+        "single_core_decompress": res[0]["n"] / res[0]["t_decomp"] / 1e9,
+        "single_core_compress": res[0]["n"] / res[0]["t_comp"] / 1e9,
+        "ratio": total / sum(r["c"] for r in res), "roundtrip_ok": all(r["ok"] for r in res),
+    }
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 6]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if v >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    base = cpu_baseline()
+    # K "steps": repeat the bounded sample; report the best-sustained aggregate
+    vals = [base["value"]]
+    for _ in range(max(0, min(args.steps, 3) - 1)):
+        if time.time() - t0 > 150:
+            break
+        vals.append(cpu_baseline()["value"])
+    v = statistics.median(vals)
+    base["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "mixed corpus (text/low-entropy/random, 1 MiB segments), decompression, "
+                               "reference CPU build on all host cores, bounded sample"},
+        "cpu_baseline": base,
+        "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "compress": {"value": base["compress_value"], "unit": "GB/s"},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def measured_peak() -> tuple[float, str]:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def run_gpu_arm(args) -> None:
+    import torch
+    import torch.distributed as dist
+    from lightweight_snappy_b200 import api, corpus
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        base = cpu_baseline()
+
+    n = int(args.gib * GIB)
+    seg0 = rank * (n >> 20)  # every rank owns its own slice of the corpus
+    data = corpus.make_corpus("mixed", n, seed=SEED, device=dev, first_segment=seg0)
+    codec = api.DeviceCodec(n, device=dev)
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- setup: one compression gives the stream every decompression step consumes
+    codec.compress(data, api.MODE_HASH)
+    stream = codec.result_stream().clone()
+    c_bytes = stream.numel()
+    side_index = codec.block_offsets.clone()
+    hdr = 1
+    while (n >> (7 * hdr)) > 0:
+        hdr += 1
+    k0_index = torch.zeros_like(side_index)
+
+    def step_decompress(ev=None):
+        codec.index(stream, c_bytes, hdr, n, k0_index)  # K0: the stream carries no block index
+        if ev:
+            ev[0].record()
+        codec.decompress_indexed(stream, k0_index, n, out)
+        if ev:
+            ev[1].record()
+
+    def step_compress(ev=None):
+        if ev:
+            ev[0].record()
+        codec.compress(data, api.MODE_HASH)
+        if ev:
+            ev[1].record()
+
+    # correctness of what is about to be timed (outside the timed region)
+    step_decompress()
+    codec.check_status()
+    assert torch.equal(out, data), "round trip failed"
+    assert torch.equal(k0_index, side_index), "K0 index differs from the compressor's side index"
+
+    def timed(step, kernel_name):
+        for _ in range(args.warmup):
+            step()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        launches0 = api.launch_count()
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for i in range(args.steps):
+            step(evs[i])
+        t_end.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        total_ms = t_start.elapsed_time(t_end)
+        kern_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+        return {"total_ms": max_over_ranks(total_ms), "kernel_ms": kern_ms, "clocks": clocks,
+                "launches": api.launch_count() - launches0, "kernel": kernel_name}
+
+    td = timed(step_decompress, "k_decode_warp")
+    codec.check_status()
+    tc = timed(step_compress, "k_compress<hash> + k_scan_sizes + k_gather")
+    codec.check_status()
+
+    # ---- end to end through the host-buffer C-ABI (pinned host memory, copies inside)
+    h_stream = torch.empty(c_bytes, dtype=torch.uint8, pin_memory=True)
+    h_stream.copy_(stream)
+    h_data = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_data.copy_(data)
+    h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_comp = torch.empty(codec.comp_capacity, dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize(dev)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def e2e(fn):
+        for _ in range(min(args.warmup, 2)):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        barrier()
+        return max_over_ranks(dt)
+
+    got = {}
+
+    def e2e_decomp():
+        got["d"] = api.decompress_host(h_stream.numpy(), out=h_out.numpy())
+
+    def e2e_comp():
+        got["c"] = api.compress_host(h_data.numpy(), api.MODE_HASH, out=h_comp.numpy())
+
+    dt_d = e2e(e2e_decomp)
+    assert got["d"].size == n and torch.equal(h_out, h_data), "e2e round trip failed"
+    dt_c = e2e(e2e_comp)
+    assert got["c"].size == c_bytes and torch.equal(h_comp[:c_bytes], h_stream), "e2e stream differs"
+
+    # ---- aggregate over ranks
+    total_u = sum_over_ranks(float(n))
+    total_c = sum_over_ranks(float(c_bytes))
+    peak, peak_src = measured_peak()
+
+    def roofline(t, per_launch_bytes):
+        achieved = per_launch_bytes / (t["kernel_ms"] * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": t["kernel"],
+                "algorithmic_bytes_per_launch": per_launch_bytes, "kernel_ms": t["kernel_ms"]}
+
+    if rank == 0:
+        ms_d = td["total_ms"] / args.steps
+        ms_c = tc["total_ms"] / args.steps
+        line = {
+            "metric": METRIC, "value": total_u * args.steps / (td["total_ms"] * 1e-3) / 1e9, "unit": "GB/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_d,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {
+                "workload": f"{args.gib:g} GiB synthetic mixed corpus per GPU (text-like/low-entropy/random, 1 MiB "
+                            f"segments), decompression of the index-less reference-format stream "
+                            f"(BASELINE configs[1]); compress{{}} = hash-table compression of the same corpus "
+                            f"(configs[2])",
+                "bytes_per_gpu": n, "compressed_bytes_per_gpu": c_bytes, "blocks_per_gpu": api.block_count(n),
+                "l2": "inputs+outputs per step (>= 1.5 GiB) are far larger than the 126 MB L2; no flush needed",
+                "partitioning": f"{world} rank(s), each owns its own corpus slice; no data-path collective",
+            },
+            "ratio": total_u / total_c,
+            "roofline": roofline(td, float(n + c_bytes)),
+            "e2e": {"value": total_u * e2e_steps / dt_d / 1e9, "unit": "GB/s", "h2d_bytes_per_step": c_bytes,
+                    "d2h_bytes_per_step": n, "steps": e2e_steps,
+                    "api": "snappy_b200_decompress_host (pinned host buffers)"},
+            "gpu_launches": td["launches"],
+            "clocks": td["clocks"],
+            "compress": {
+                "value": total_u * args.steps / (tc["total_ms"] * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_c,
+                "roofline": roofline(tc, float(n + c_bytes)),
+                "e2e": {"value": total_u * e2e_steps / dt_c / 1e9, "unit": "GB/s", "h2d_bytes_per_step": n,
+                        "d2h_bytes_per_step": c_bytes, "api": "snappy_b200_compress_host (pinned host buffers)"},
+                "gpu_launches": tc["launches"], "clocks": tc["clocks"],
+                "parity": "stream byte-identical to the oracle is asserted in tests/ and smoke(); here the "
+                          "round trip and the K0 index are asserted before timing",
+            },
+        }
+        if base is not None:
+            line["cpu_baseline"] = base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gib", type=float, default=1.0, help="corpus size per GPU in GiB")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,8 @@ const char *snappy_b200_last_error(void);
 int snappy_b200_device_count(void);
 /* How many kernels this library has launched in this process (bench.py's gpu_launches). */
 uint64_t snappy_b200_launch_count(void);
+/* Relaxation rounds the last snappy_b200_index_device call needed (diagnostic). */
+uint64_t snappy_b200_index_rounds(void);
 
 /* Upper bound of the stream for n input bytes: 10 + n + 1010 per block (src :180-190). */
 uint64_t snappy_b200_max_compressed_bytes(uint64_t n_bytes);
@@ -89,7 +91,9 @@ int snappy_b200_compress_device(const uint8_t *d_in, uint64_t n_bytes, int mode,
                                 uint32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Decodes n_blocks blocks whose stream offsets are given (d_block_offsets[n_blocks+1]);
- * block i produces bytes [i*65536, min(total_out, (i+1)*65536)) of d_out.               */
+ * block i produces bytes [i*65536, min(total_out, (i+1)*65536)) of d_out.  *d_status is
+ * OR-ed into, not reset: the caller zeroes it, and a non-zero status on entry (e.g. left by
+ * a failed snappy_b200_index_device on the same stream) turns the call into a no-op.     */
 int snappy_b200_decompress_device_indexed(const uint8_t *d_stream, const uint64_t *d_block_offsets,
                                           uint64_t n_blocks, uint64_t total_out, uint8_t *d_out,
                                           uint32_t *d_status, void *stream);

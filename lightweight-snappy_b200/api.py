@@ -37,6 +37,7 @@ SIGNATURES = {
     "snappy_b200_last_error": (C.c_char_p, []),
     "snappy_b200_device_count": (C.c_int, []),
     "snappy_b200_launch_count": (C.c_uint64, []),
+    "snappy_b200_index_rounds": (C.c_uint64, []),
     "snappy_b200_max_compressed_bytes": (C.c_uint64, [C.c_uint64]),
     "snappy_b200_block_count": (C.c_uint64, [C.c_uint64]),
     "snappy_b200_compress_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_int]),
@@ -221,6 +222,10 @@ class DeviceCodec:
         st = int(self.status.item())
         if st:
             raise SnappyError(-st, f"device status 0x{st:x}")
+
+
+def index_rounds() -> int:
+    return int(lib().snappy_b200_index_rounds())
 
 
 def launch_count() -> int:

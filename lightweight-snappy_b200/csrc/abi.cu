@@ -18,6 +18,7 @@ size_t index_workspace_bytes(uint64_t);
 cudaError_t run_index(const uint8_t *, uint64_t, uint64_t, uint64_t, uint64_t *, uint32_t *, void *, cudaStream_t,
                       uint64_t *);
 uint32_t host_varint_len(uint64_t);
+uint64_t index_last_rounds();
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
@@ -93,6 +94,8 @@ int snappy_b200_device_count(void)
 }
 
 uint64_t snappy_b200_launch_count(void) { return g_launches.load(); }
+
+uint64_t snappy_b200_index_rounds(void) { return index_last_rounds(); }
 
 uint64_t snappy_b200_block_count(uint64_t n_bytes) { return (n_bytes + kBlock - 1) / kBlock; }
 

@@ -11,16 +11,20 @@
 //                      and the offset at which it leaves the segment.  Snappy streams
 //                      re-synchronise within a few elements, so most of these walks merge
 //                      into the true element chain long before the segment ends.
-//   B  k_index_scatter / k_index_apply   relaxation rounds.  Every segment that currently
-//                      believes it holds an element start publishes its exit to the segment
-//                      it lands in (and marks the segments a long literal jumps over as
-//                      holding none); when several segments disagree the lowest source wins.
-//                      A segment whose entry changed re-walks from the new entry until it
-//                      meets its old path.  Segment 0's entry is known, so the beliefs are
-//                      correct on a prefix that grows every round; a round that changes
-//                      nothing is the unique fixed point = the true chain.  Typical streams
-//                      need 2-3 rounds; an adversarial one degrades to sequential but stays
-//                      correct.
+//   B  k_index_scatter / k_index_apply   relaxation rounds.  Every segment publishes the exit
+//                      of its current walk to the segment it lands in, and a live segment marks
+//                      the segments a long literal jumps over as "dead" (holding no element
+//                      start).  A segment that was itself marked dead keeps publishing its exit,
+//                      but at low priority; among equal priorities the lowest source wins.  A segment
+//                      whose entry changed re-walks from the new entry until it meets its old
+//                      path.  Segment 0's entry is known, every other segment is claimed or
+//                      marked by a live predecessor, so the beliefs are correct on a prefix
+//                      that grows every round, and a round that changes nothing is the unique
+//                      fixed point = the true chain.  Keeping dead segments talking matters:
+//                      when a mis-speculated "long literal" wrongly kills a run of segments,
+//                      they all come back in the round after it is corrected instead of one
+//                      per round.  Typical streams need 3-4 rounds; an adversarial one
+//                      degrades to sequential but stays correct.
 //   C  k_index_outlen  every live segment sums the output bytes of its elements
 //      k_scan_u64      exclusive scan -> output offset of every segment
 //   D  k_index_blocks  every live segment walks once more and records the stream offset of
@@ -32,7 +36,9 @@
 namespace sb200 {
 
 constexpr uint32_t kSeg = 128;          // bytes of stream per segment
-constexpr uint32_t kNoEntry = 0xffu;    // E[t]: the segment holds no element start
+constexpr uint32_t kDead = 0x80u;       // entry[t] bit 7: no element starts here (bits 0-6 keep the last entry)
+constexpr uint32_t kMark = 0xffu;       // claim payload: "a literal jumps over you"
+constexpr unsigned long long kLowPrio = 1ull << 63;
 constexpr unsigned long long kNone = ~0ull;
 
 struct Elem {
@@ -136,18 +142,27 @@ __global__ void __launch_bounds__(256) k_index_scatter(uint64_t body_len, uint64
                                                        unsigned long long *__restrict__ claim)
 {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (t >= nseg || entry[t] == kNoEntry)
+    if (t >= nseg)
         return;
+    const bool dead = entry[t] & kDead;
+    const unsigned long long prio = dead ? kLowPrio : 0ull;
     const uint64_t x = exits[t];
     const uint64_t u = x / kSeg; // segment the chain lands in
-    // Segments jumped over hold no element start.  An element of this framing never spans more
-    // than one 64 KiB block (+ header), which bounds the work a mis-speculated "huge literal"
-    // can cause; a true element that long is reported as SNAPPY_B200_ST_FRAMING by k_index_outlen.
-    const uint64_t vmax = min(min(u, nseg), t + 1 + (kBlock + 1024) / kSeg);
-    for (uint64_t v = t + 1; v < vmax; ++v)
-        atomicMin(claim + v, (unsigned long long)((t << 8) | kNoEntry));
+    if (!dead) {
+        // Segments jumped over hold no element start (only a live source may say so: a dead
+        // segment's walk is pure speculation, and its bogus "huge literals" would otherwise keep
+        // killing true segments round after round).  An element of this framing never spans
+        // more than one 64 KiB block (+ header), which bounds the work a mis-speculated literal
+        // can cause; a true element that long is reported as SNAPPY_B200_ST_FRAMING by
+        // k_index_outlen.
+        const uint64_t vmax = min(min(u, nseg), t + 1 + (kBlock + 1024) / kSeg);
+        for (uint64_t v = t + 1; v < vmax; ++v)
+            atomicMin(claim + v, (unsigned long long)((t << 8) | kMark));
+        if (u < nseg && x >= body_len) // the chain ends inside the last segment: nothing starts there
+            atomicMin(claim + u, (unsigned long long)((t << 8) | kMark));
+    }
     if (u < nseg && x < body_len)
-        atomicMin(claim + u, (unsigned long long)((t << 8) | (x - u * kSeg)));
+        atomicMin(claim + u, prio | (unsigned long long)((t << 8) | (x - u * kSeg)));
 }
 
 __global__ void __launch_bounds__(256) k_index_apply(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
@@ -161,14 +176,21 @@ __global__ void __launch_bounds__(256) k_index_apply(const uint8_t *__restrict__
         return;
     const unsigned long long c = claim[t];
     claim[t] = kNone; // ready for the next round
-    const uint32_t ne = t == 0 ? 0u : (c == kNone ? kNoEntry : (uint32_t)(c & 0xffu));
     const uint32_t old = entry[t];
+    const uint32_t payload = (uint32_t)(c & 0xffu);
+    uint32_t ne;
+    if (t == 0)
+        ne = 0; // the body starts with an element
+    else if (c == kNone || payload == kMark)
+        ne = (old & 0x7fu) | kDead;
+    else
+        ne = payload;
     if (ne == old)
         return;
     entry[t] = (uint8_t)ne;
     atomicOr(changed, 1u);
-    if (ne == kNoEntry)
-        return;
+    if ((ne & kDead) || (ne & 0x7fu) == (old & 0x7fu))
+        return; // dead, or revived with the entry it already walked from
     const uint64_t lo = t * kSeg;
     const uint64_t hi = min(lo + kSeg, body_len);
     const uint4 pv = paths[t];
@@ -199,7 +221,7 @@ __global__ void __launch_bounds__(256) k_index_outlen(const uint8_t *__restrict_
         return;
     uint64_t sum = 0;
     const uint32_t en = entry[t];
-    if (en != kNoEntry) {
+    if (!(en & kDead)) {
         const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
         uint64_t e = lo + en;
         while (e < hi) {
@@ -285,7 +307,7 @@ __global__ void __launch_bounds__(256) k_index_blocks(const uint8_t *__restrict_
     if (t >= nseg)
         return;
     const uint32_t en = entry[t];
-    if (en == kNoEntry)
+    if (en & kDead)
         return;
     const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
     uint64_t e = lo + en, op = outoff[t];
@@ -359,6 +381,9 @@ static IndexWorkspace carve(void *ws, uint64_t stream_bytes)
     return w;
 }
 
+static uint64_t g_last_rounds = 0;
+uint64_t index_last_rounds() { return g_last_rounds; }
+
 // Synchronises the stream between relaxation rounds (it has to read the "changed" flag).
 cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset, uint64_t total_out,
                       uint64_t *d_block_offsets, uint32_t *d_status, void *d_ws, cudaStream_t st, uint64_t *launches)
@@ -379,20 +404,33 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
     k_fill_u64<<<grid, 256, 0, st>>>(w.claim, nseg, kNone);
     k_index_spec<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits, w.entry);
     *launches += 2;
-    const uint64_t max_rounds = nseg + 2;
-    for (uint64_t round = 0; round < max_rounds; ++round) {
-        if ((e = cudaMemsetAsync(w.changed, 0, 4, st)) != cudaSuccess)
+    // The "did anything change" flag is only read back every kCheck rounds: a round costs two
+    // short kernels, a host round trip costs more.
+    constexpr uint64_t kCheck = 4;
+    const uint64_t max_rounds = nseg + 2 + kCheck;
+    if ((e = cudaMemsetAsync(w.changed, 0, 4 * kCheck, st)) != cudaSuccess)
+        return e;
+    for (uint64_t round = 0; round < max_rounds; round += kCheck) {
+        for (uint64_t k = 0; k < kCheck; ++k) {
+            k_index_scatter<<<grid, 256, 0, st>>>(body_len, nseg, w.exits, w.entry, w.claim);
+            k_index_apply<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits, w.entry, w.claim,
+                                                w.changed + k);
+        }
+        *launches += 2 * kCheck;
+        uint32_t changed[kCheck];
+        if ((e = cudaMemcpyAsync(changed, w.changed, 4 * kCheck, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+            (e = cudaMemsetAsync(w.changed, 0, 4 * kCheck, st)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(st)) != cudaSuccess)
             return e;
-        k_index_scatter<<<grid, 256, 0, st>>>(body_len, nseg, w.exits, w.entry, w.claim);
-        k_index_apply<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits, w.entry, w.claim, w.changed);
-        *launches += 2;
-        uint32_t changed = 0;
-        if ((e = cudaMemcpyAsync(&changed, w.changed, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
-            return e;
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess)
-            return e;
-        if (!changed)
+        g_last_rounds = round + kCheck;
+        if (!changed[kCheck - 1]) { // a round without change is the fixed point
+            for (uint64_t k = 0; k < kCheck; ++k)
+                if (!changed[k]) {
+                    g_last_rounds = round + k + 1;
+                    break;
+                }
             break;
+        }
     }
     k_index_outlen<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outlen, d_status);
     k_scan_u64<<<1, 1024, 0, st>>>(w.outlen, nseg, w.outoff, w.total);
