@@ -9,7 +9,9 @@
 #include "common.cuh"
 
 namespace sb200 {
-cudaError_t launch_compress(const uint8_t *, uint64_t, int, uint8_t *, uint32_t *, cudaStream_t, uint64_t *);
+cudaError_t launch_compress(const uint8_t *, uint64_t, int, uint8_t *, uint32_t *, uint2 *, uint32_t *, cudaStream_t,
+                            uint64_t *);
+size_t compress_records_bytes(uint64_t);
 cudaError_t launch_compact(const uint8_t *, const uint32_t *, uint64_t, uint64_t, uint64_t, int, uint8_t *, uint64_t,
                            uint64_t *, uint64_t *, uint32_t *, cudaStream_t, uint64_t *);
 cudaError_t launch_decode(const uint8_t *, const uint64_t *, uint64_t, uint64_t, uint8_t *, uint32_t *, cudaStream_t,
@@ -41,15 +43,18 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 struct CompressWorkspace {
-    uint8_t *scratch;
-    uint32_t *sizes;
-    uint64_t *offsets;
+    uint8_t *scratch;   // one 66560-byte slot per block: the block's compressed bytes
+    uint2 *recs;        // one 8-byte record per copy, 16384 per block
+    uint32_t *sizes;    // compressed size of every block
+    uint32_t *nrec;     // records of every block
+    uint64_t *offsets;  // stream offset of every block (when the caller does not want them)
 };
 
 static size_t compress_ws_bytes(uint64_t n_bytes)
 {
     const uint64_t nb = (n_bytes + kBlock - 1) / kBlock;
-    return align_up(nb * (size_t)kSlot + 64, 256) + align_up(nb * 4 + 4, 256) + align_up((nb + 1) * 8, 256);
+    return align_up(nb * (size_t)kSlot + 64, 256) + align_up(compress_records_bytes(nb) + 64, 256) +
+           2 * align_up(nb * 4 + 4, 256) + align_up((nb + 1) * 8, 256);
 }
 
 static CompressWorkspace carve_compress(void *ws, uint64_t n_bytes)
@@ -58,7 +63,9 @@ static CompressWorkspace carve_compress(void *ws, uint64_t n_bytes)
     uint8_t *p = static_cast<uint8_t *>(ws);
     CompressWorkspace w;
     w.scratch = p, p += align_up(nb * (size_t)kSlot + 64, 256);
+    w.recs = reinterpret_cast<uint2 *>(p), p += align_up(compress_records_bytes(nb) + 64, 256);
     w.sizes = reinterpret_cast<uint32_t *>(p), p += align_up(nb * 4 + 4, 256);
+    w.nrec = reinterpret_cast<uint32_t *>(p), p += align_up(nb * 4 + 4, 256);
     w.offsets = reinterpret_cast<uint64_t *>(p);
     return w;
 }
@@ -135,7 +142,7 @@ int snappy_b200_compress_device(const uint8_t *d_in, uint64_t n_bytes, int mode,
     }
     CompressWorkspace w = carve_compress(d_workspace, n_bytes);
     uint64_t launches = 0;
-    e = launch_compress(d_in, n_bytes, mode, w.scratch, w.sizes, st, &launches);
+    e = launch_compress(d_in, n_bytes, mode, w.scratch, w.sizes, w.recs, w.nrec, st, &launches);
     if (e == cudaSuccess)
         e = launch_compact(w.scratch, w.sizes, nb, n_bytes, host_varint_len(n_bytes), 1, d_out, out_capacity,
                            d_block_offsets ? d_block_offsets : w.offsets, d_out_bytes, d_status, st, &launches);

@@ -1,102 +1,45 @@
-// compress.cu -- K1 (hash-table parse) and K2 (exact-key parse): one warp per 64 KiB block.
+// compress.cu -- K1 (hash-table parse), K2 (exact-key parse) and K1e (element emission).
 //
 // What is computed is exactly the greedy parse of the reference
 //   hash mode : src/snappy_compression.c:384-403 (compress_next_block)
 //   exact mode: src/snappy_compression_tree.c:269-288 with the dictionary of src/BST.c
-// and the element encodings of src/snappy_compression.c:95-165.  How it is computed is not:
+// and the element encodings of src/snappy_compression.c:95-165.  How it is computed is not.
 //
-// The parse is serial in the table state, so a warp speculates.  Each step lays the next 16
+// k_parse -- one warp per 64 KiB block; the serial part, kept as lean as possible.
+// The parse is serial in the table state, so the warp speculates.  Each step lays the next 16
 // probe positions out as 32 "events" (lane 2j = the p-1 insertion that probe j would make on
 // a miss, lane 2j+1 = probe j itself), under the assumption that every earlier probe of the
 // step misses.  Lanes look their key up in the shared-memory table AND in the earlier lanes
 // of the same step (__match_any_sync), which reproduces what the table would hold after
 // those misses.  The first probe that hits (or reaches the end-of-block test) cuts the step:
-// the misses before it are committed to the table in one go, the hit is extended with a
-// warp-wide 4-byte-per-lane compare, and literal + copy elements are emitted.  Everything the
-// speculation assumed about lanes after the cut is simply discarded, so the result is the
-// reference's parse, bit for bit.
+// the misses before it are committed to the table in one go and the hit is extended with a
+// warp-wide 4-byte-per-lane compare.  Everything the speculation assumed about lanes after
+// the cut is discarded, so the result is the reference's parse, bit for bit.  The warp does
+// not write compressed bytes: it leaves one 8-byte record per copy {position, offset,
+// length, literal run before it}.
 //
 // Hash-mode table entry: (16-bit key fingerprint << 16) | u16 position.  The fingerprint is
 // bits 19..4 of key*0x1e35a7bd -- together with the 12-bit slot index it pins 28 of the 32
 // bits of an injective function of the key, so the "does the candidate's 4 bytes equal mine"
-// test of the reference (found_match, :259-265) is answered from shared memory; the candidate
-// bytes are only fetched to confirm the one lane that wins.  The reference's zero-filled
-// table ("candidate = position 0") becomes (fingerprint of the block's first 4 bytes, 0).
+// test of the reference (found_match, :259-265) is almost always answered from shared memory;
+// lanes whose fingerprint matches confirm against the candidate bytes, all at once.  The
+// reference's zero-filled table ("candidate = position 0") becomes (fingerprint of the
+// block's first 4 bytes, 0).
 //
 // Exact mode keeps an open-addressing table of u16 positions keyed by the exact 4 bytes
 // (0xffff = empty, which no insertable position can be: positions >= n-15 are never probed).
 // Keys are compared through the block itself.  Tables come in three sizes; a block whose
 // dictionary outgrows the small table is marked and redone by the next tier.
+//
+// k_emit -- one CTA per block, one thread per record: literal header + bytes and the copy
+// tags (write_literal :95-120, write_copy :153-165, write_single_copy :131-145) are sized,
+// prefix-summed and written in parallel into the block's scratch slot; long literals are
+// copied by the whole CTA with 16-byte stores.
 #include "common.cuh"
 
 namespace sb200 {
 
-// ------------------------------------------------------------------------------- emission
-// reference: write_literal, src/snappy_compression.c:95-120
-__device__ __forceinline__ void emit_literal(const uint8_t *__restrict__ b, uint32_t src, uint32_t len,
-                                             uint8_t *__restrict__ out, uint32_t &o, uint32_t lane)
-{
-    const uint32_t m = len - 1;
-    uint32_t hdr;
-    if (m < 60) {
-        hdr = 1;
-        if (lane == 0)
-            out[o] = (uint8_t)(m << 2);
-    } else if (m < 256) {
-        hdr = 2;
-        if (lane == 0) {
-            out[o] = 60u << 2;
-            out[o + 1] = (uint8_t)m;
-        }
-    } else { // m <= 65535 inside a 64 KiB block
-        hdr = 3;
-        if (lane == 0) {
-            out[o] = 61u << 2;
-            out[o + 1] = (uint8_t)m;
-            out[o + 2] = (uint8_t)(m >> 8);
-        }
-    }
-    coop_copy_ro(out + o + hdr, b + src, len, lane, 32);
-    o += hdr + len;
-}
-
-// reference: write_copy :153-165 and write_single_copy :131-145
-__device__ __forceinline__ void emit_copy(uint8_t *__restrict__ out, uint32_t &o, uint32_t len, uint32_t off,
-                                          uint32_t lane)
-{
-    const uint32_t n64 = len > 68 ? (len - 5) / 64 : 0; // "while (len > 68) emit 64"
-    uint32_t rem = len - 64 * n64;
-    for (uint32_t k = lane; k < n64; k += 32) {
-        uint8_t *p = out + o + 3 * k;
-        p[0] = 0xfe; // ((64-1) << 2) | 2
-        p[1] = (uint8_t)off;
-        p[2] = (uint8_t)(off >> 8);
-    }
-    o += 3 * n64;
-    if (rem > 64) { // 64 < rem <= 68: emit 60 so that at least 4 remain
-        if (lane == 0) {
-            out[o] = 0xee; // ((60-1) << 2) | 2
-            out[o + 1] = (uint8_t)off;
-            out[o + 2] = (uint8_t)(off >> 8);
-        }
-        o += 3;
-        rem -= 60;
-    }
-    if (rem < 12 && off < 2048) {
-        if (lane == 0) {
-            out[o] = (uint8_t)(((off >> 8) << 5) + ((rem - 4) << 2) + 1);
-            out[o + 1] = (uint8_t)off;
-        }
-        o += 2;
-    } else {
-        if (lane == 0) {
-            out[o] = (uint8_t)(((rem - 1) << 2) | 2);
-            out[o + 1] = (uint8_t)off;
-            out[o + 2] = (uint8_t)(off >> 8);
-        }
-        o += 3;
-    }
-}
+constexpr uint32_t kMaxRecords = 16384; // a copy covers >= 4 bytes
 
 // reference: find_copy_length :61-72 (+4 for the bytes the probe already matched).
 // Lane l compares bytes [base+4l, base+4l+4) of the two strings; the first lane that sees a
@@ -174,26 +117,25 @@ template <int LOG_SLOTS> struct ExactTable {
     }
 };
 
-// ------------------------------------------------------------------------------- the kernel
+// ------------------------------------------------------------------------------- the parse
 // MODE 0 = hash table (LOG_SLOTS ignored: the table has up to 4096 u32 entries)
 // MODE 1 = exact dictionary with 2^LOG_SLOTS u16 slots; a block whose dictionary would grow
-//          past 3/4 of the table gives up (sizes[blk] = kAbortMark) unless FINAL.
+//          past 3/4 of the table gives up (nrec[blk] = kAbortMark) unless FINAL.
 template <int MODE, int LOG_SLOTS, bool FINAL>
-__global__ void __launch_bounds__(32) k_compress(const uint8_t *__restrict__ in, uint64_t n_bytes,
-                                                 uint8_t *__restrict__ scratch, uint32_t *__restrict__ sizes,
-                                                 int only_marked)
+__global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, uint64_t n_bytes,
+                                              uint2 *__restrict__ recs, uint32_t *__restrict__ nrec, int only_marked)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = threadIdx.x;
     const uint64_t blk = blockIdx.x;
-    if (only_marked && sizes[blk] != kAbortMark)
+    if (only_marked && nrec[blk] != kAbortMark)
         return;
 
     const uint8_t *__restrict__ b = in + blk * (uint64_t)kBlock;
     const uint64_t left = n_bytes - blk * (uint64_t)kBlock;
     const uint32_t n = left < kBlock ? (uint32_t)left : kBlock;
     const uint32_t last_word = (n - 1) >> 2;
-    uint8_t *__restrict__ out = scratch + blk * (uint64_t)kSlot;
+    uint2 *__restrict__ my_recs = recs + blk * (uint64_t)kMaxRecords;
 
     // per-miss skip bookkeeping: hash mode skip += 1 per miss and the step uses the value the
     // end test saw (:229-232, :283-287); BST mode post-increments inside the end test as well
@@ -212,8 +154,8 @@ __global__ void __launch_bounds__(32) k_compress(const uint8_t *__restrict__ in,
         while ((1u << lg) < SNAPPY_B200_HTABLE_SIZE && (1u << lg) < n)
             ++lg;
         shift = 32 - lg;
-        const uint32_t fp0 = n >= 4 ? ((ld_be32(b, 0, last_word) * kHashMul) >> 4) & 0xffffu : 0;
-        const uint4 init = make_uint4(fp0 << 16, fp0 << 16, fp0 << 16, fp0 << 16);
+        const uint32_t e0 = n >= 4 ? ((ld_be32(b, 0, last_word) * kHashMul) << 12) & 0xffff0000u : 0;
+        const uint4 init = make_uint4(e0, e0, e0, e0);
         uint4 *t4 = reinterpret_cast<uint4 *>(htab);
         for (uint32_t i = lane; i < (1u << lg) / 4; i += 32)
             t4[i] = init;
@@ -225,10 +167,12 @@ __global__ void __launch_bounds__(32) k_compress(const uint8_t *__restrict__ in,
     }
     __syncwarp();
 
-    uint32_t pos = 1, skip = 33, lit_start = 0, o = 0; // :386-387: the first byte is a literal
+    uint32_t pos = 1, skip = 33, prev_end = 0; // :386-387: the first byte is a literal
+    uint32_t nh = 0;                           // records so far
+    uint2 rec = make_uint2(0, 0);              // lane (nh & 31) holds record nh until 32 are full
 
     const uint32_t j = lane >> 1;
-    const bool is_probe = lane & 1u;
+    const uint32_t odd = lane & 1u; // odd lanes are the probes
     const unsigned vis_mask = lane >= 1 ? (1u << (lane - 1)) - 1u : 0u; // events a probe may see
 
     for (;;) {
@@ -238,29 +182,33 @@ __global__ void __launch_bounds__(32) k_compress(const uint8_t *__restrict__ in,
         const uint32_t k1 = (32u - r + C - 1u) / C; // first probe index whose step is q+1
         const uint32_t pj = pos + j * q + (j > k1 ? j - k1 : 0u);
         const bool end_j = pj + ((skip + C * j) >> 5) + 15u > n; // is_block_end
-        const uint32_t ev_pos = is_probe ? pj : pj - 1;
+        const uint32_t ev_pos = pj - 1 + odd;
         const uint32_t key = ld_be32(b, end_j ? 0u : ev_pos, last_word);
+        const bool probe = odd && !end_j;
 
-        bool cand_hit;   // this lane's probe would hit (hash mode: still to be confirmed)
-        bool forwarded;  // ... through an earlier event of the same step
-        uint32_t cand;   // candidate position
-        uint32_t idx = 0, fpv = 0;
+        bool hit;       // this lane's probe hits
+        uint32_t cand;  // ... this candidate position
+        uint32_t idx = 0, ph = 0;
         unsigned grp;
         bool in_table = false;
 
         if (MODE == 0) {
             const uint32_t prod = key * kHashMul; // hash_bytes :81-84
             idx = prod >> shift;
-            fpv = (prod >> 4) & 0xffffu;
+            ph = (prod << 12) & 0xffff0000u;
             grp = __match_any_sync(kFull, idx);
             const unsigned vis = grp & vis_mask;
-            const int src = vis ? 31 - __clz((int)vis) : 0; // latest earlier writer of the slot
+            const int src = 31 - __clz((int)vis); // latest earlier writer of the slot (-1: none)
             const uint32_t skey = __shfl_sync(kFull, key, src);
             const uint32_t spos = __shfl_sync(kFull, ev_pos, src);
             const uint32_t entry = htab[idx];
-            forwarded = vis != 0;
-            cand_hit = forwarded ? skey == key : (entry >> 16) == fpv;
-            cand = forwarded ? spos : entry & 0xffffu;
+            if (vis) {
+                hit = skey == key;
+                cand = spos;
+            } else {
+                cand = entry & 0xffffu;
+                hit = probe && ((entry ^ ph) < 0x10000u) && ld_be32(b, cand, last_word) == key; // found_match :259-265
+            }
         } else {
             grp = __match_any_sync(kFull, key);
             const unsigned vis = grp & vis_mask;
@@ -269,58 +217,41 @@ __global__ void __launch_bounds__(32) k_compress(const uint8_t *__restrict__ in,
             uint32_t tpos = 0;
             if (!end_j)
                 (void)et.find(b, last_word, key, in_table, tpos);
-            forwarded = !in_table && vis != 0;
-            cand_hit = in_table || forwarded;
+            hit = in_table || vis != 0;
             cand = in_table ? tpos : spos;
         }
 
-        unsigned H = __ballot_sync(kFull, is_probe && !end_j && cand_hit);
-        const unsigned E = __ballot_sync(kFull, is_probe && end_j);
-        const int first_end = E ? __ffs((int)E) - 1 : 32;
-        if (first_end < 32)
-            H &= (1u << first_end) - 1u;
-
-        // ---- first real hit
-        int f = -1;
-        while (H) {
-            const int c = __ffs((int)H) - 1;
-            bool ok = true;
-            if (MODE == 0) {
-                const uint32_t ccand = __shfl_sync(kFull, cand, c);
-                const uint32_t ckey = __shfl_sync(kFull, key, c);
-                const bool cfwd = __shfl_sync(kFull, (int)forwarded, c);
-                ok = cfwd || ld_be32(b, ccand, last_word) == ckey; // found_match :259-265
-            }
-            if (ok) {
-                f = c;
-                break;
-            }
-            H &= H - 1; // fingerprint collision: that probe is a miss after all
-        }
-
+        const unsigned H = __ballot_sync(kFull, probe && hit);
+        const unsigned E = __ballot_sync(kFull, odd && end_j);
+        const unsigned HE = H | E;
         // ---- commit the misses before the cut (the cut probe's own p-1 event is not one)
-        const int L = f >= 0 ? f - 1 : (first_end < 32 ? first_end - 1 : 32);
-        const unsigned cm = L >= 32 ? kFull : (1u << L) - 1u;
+        const int f = HE ? __ffs((int)HE) - 1 : 33;
+        const unsigned cm = f >= 33 ? kFull : (1u << (f - 1)) - 1u;
         const unsigned g = grp & cm;
         if (MODE == 0) {
             // update_hash_table :303-307: in program order the last writer of a slot wins
-            if ((int)lane < L && 31 - __clz((int)g) == (int)lane)
-                htab[idx] = (fpv << 16) | ev_pos;
+            if (g && 31 - __clz((int)g) == (int)lane)
+                htab[idx] = ph | ev_pos;
         } else {
             // insert-if-absent, src/BST.c:30-43: the first occurrence of a new key is kept
-            const bool ins = (int)lane < L && !in_table && __ffs((int)g) - 1 == (int)lane;
+            const bool ins = g && !in_table && __ffs((int)g) - 1 == (int)lane;
             if (ins)
                 et.insert_absent(key, ev_pos);
             n_keys += __popc(__ballot_sync(kFull, ins));
         }
-        __syncwarp();
 
-        if (f >= 0) {
+        if (HE == 0) {
+            pos += 16 * q + (16 > k1 ? 16 - k1 : 0u); // 16 x append_literal :283-287
+            skip += 16 * C;
+        } else if (!((H >> f) & 1u)) {
+            break; // the end-of-block test fired first
+        } else {
+            __syncwarp();
             const uint32_t p = __shfl_sync(kFull, ev_pos, f);
             const uint32_t c = __shfl_sync(kFull, cand, f);
             if (MODE == 0) {
                 if ((int)lane == f)
-                    htab[idx] = (fpv << 16) | ev_pos; // emit_copy :327
+                    htab[idx] = ph | ev_pos; // emit_copy :327
             } else {
                 if ((int)lane == f) { // tree.c:221: the found node now points at this position
                     bool fnd;
@@ -329,39 +260,200 @@ __global__ void __launch_bounds__(32) k_compress(const uint8_t *__restrict__ in,
                     et.tab[s] = (uint16_t)ev_pos;
                 }
             }
-            if (p > lit_start)
-                emit_literal(b, lit_start, p - lit_start, out, o, lane); // emit_literal :313-316
             const uint32_t len = match_extend(b, p, c, n, last_word, lane);
-            emit_copy(out, o, len, p - c, lane);
+            if (lane == (nh & 31u))
+                rec = make_uint2(p | ((p - c) << 16), len | ((p - prev_end) << 16));
+            ++nh;
+            if ((nh & 31u) == 0)
+                my_recs[nh - 32 + lane] = rec;
             pos = p + len;
-            lit_start = pos;
+            prev_end = pos;
             skip = 32; // start_new_literal :271-274
             __syncwarp();
-        } else if (first_end < 32) {
-            break;
-        } else {
-            pos += 16 * q + (16 > k1 ? 16 - k1 : 0u); // 16 x append_literal :283-287
-            skip += 16 * C;
         }
 
         if (MODE == 1 && !FINAL && n_keys > (ExactTable<LOG_SLOTS>::kSlots * 3) / 4) {
             if (lane == 0)
-                sizes[blk] = kAbortMark;
+                nrec[blk] = kAbortMark;
             return;
         }
     }
-
-    if (n > lit_start)
-        emit_literal(b, lit_start, n - lit_start, out, o, lane); // exhaust_input :292-297, :401-402
+    if (lane < (nh & 31u))
+        my_recs[(nh & ~31u) + lane] = rec;
     if (lane == 0)
-        sizes[blk] = o;
+        nrec[blk] = nh;
+}
+
+// ------------------------------------------------------------------------------- emission
+constexpr int kEmitThreads = 128;
+constexpr uint32_t kCoopLiteral = 48; // literals at least this long are copied by the whole CTA
+
+// reference: write_literal :95-120 -- header bytes for a literal of len (>0) bytes
+__device__ __forceinline__ uint32_t literal_header(uint32_t len, uint8_t *__restrict__ o)
+{
+    const uint32_t m = len - 1;
+    if (m < 60) {
+        o[0] = (uint8_t)(m << 2);
+        return 1;
+    }
+    if (m < 256) {
+        o[0] = 60u << 2;
+        o[1] = (uint8_t)m;
+        return 2;
+    }
+    o[0] = 61u << 2; // m <= 65535 inside a 64 KiB block
+    o[1] = (uint8_t)m;
+    o[2] = (uint8_t)(m >> 8);
+    return 3;
+}
+
+__device__ __forceinline__ uint32_t literal_size(uint32_t len)
+{
+    return len == 0 ? 0 : len + (len <= 60 ? 1 : (len <= 256 ? 2 : 3));
+}
+
+// reference: write_copy :153-165 / write_single_copy :131-145
+__device__ __forceinline__ uint32_t copy_size(uint32_t len, uint32_t off)
+{
+    const uint32_t n64 = len > 68 ? (len - 5) / 64 : 0; // "while (len > 68) emit 64"
+    uint32_t rem = len - 64 * n64, sz = 3 * n64;
+    if (rem > 64) { // 64 < rem <= 68: emit 60 so that at least 4 remain
+        sz += 3;
+        rem -= 60;
+    }
+    return sz + ((rem < 12 && off < 2048) ? 2 : 3);
+}
+
+__device__ __forceinline__ void copy_emit(uint32_t len, uint32_t off, uint8_t *__restrict__ o)
+{
+    const uint32_t n64 = len > 68 ? (len - 5) / 64 : 0;
+    uint32_t rem = len - 64 * n64;
+    for (uint32_t k = 0; k < n64; ++k) {
+        o[0] = 0xfe; // ((64-1) << 2) | 2
+        o[1] = (uint8_t)off;
+        o[2] = (uint8_t)(off >> 8);
+        o += 3;
+    }
+    if (rem > 64) {
+        o[0] = 0xee; // ((60-1) << 2) | 2
+        o[1] = (uint8_t)off;
+        o[2] = (uint8_t)(off >> 8);
+        o += 3;
+        rem -= 60;
+    }
+    if (rem < 12 && off < 2048) {
+        o[0] = (uint8_t)(((off >> 8) << 5) + ((rem - 4) << 2) + 1);
+        o[1] = (uint8_t)off;
+    } else {
+        o[0] = (uint8_t)(((rem - 1) << 2) | 2);
+        o[1] = (uint8_t)off;
+        o[2] = (uint8_t)(off >> 8);
+    }
+}
+
+__global__ void __launch_bounds__(kEmitThreads) k_emit(const uint8_t *__restrict__ in, uint64_t n_bytes,
+                                                       const uint2 *__restrict__ recs,
+                                                       const uint32_t *__restrict__ nrec,
+                                                       uint8_t *__restrict__ scratch, uint32_t *__restrict__ sizes)
+{
+    __shared__ uint32_t warp_sum[kEmitThreads / 32 + 1];
+    __shared__ uint32_t q_src[kEmitThreads], q_dst[kEmitThreads], q_len[kEmitThreads];
+    __shared__ uint32_t q_n;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t blk = blockIdx.x;
+    const uint8_t *__restrict__ b = in + blk * (uint64_t)kBlock;
+    const uint64_t left = n_bytes - blk * (uint64_t)kBlock;
+    const uint32_t n = left < kBlock ? (uint32_t)left : kBlock;
+    const uint2 *__restrict__ my_recs = recs + blk * (uint64_t)kMaxRecords;
+    uint8_t *__restrict__ out = scratch + blk * (uint64_t)kSlot;
+    const uint32_t nr = nrec[blk];
+
+    uint32_t carry = 0;    // bytes emitted by earlier chunks
+    uint32_t last_end = 0; // end of the last copy: where the tail literal starts
+    for (uint32_t base = 0; base < nr; base += kEmitThreads) {
+        if (tid == 0)
+            q_n = 0;
+        const uint32_t i = base + tid;
+        uint32_t p = 0, off = 0, len = 0, lit = 0, sz = 0;
+        if (i < nr) {
+            const uint2 rc = my_recs[i];
+            p = rc.x & 0xffffu, off = rc.x >> 16, len = rc.y & 0xffffu, lit = rc.y >> 16;
+            sz = literal_size(lit) + copy_size(len, off);
+        }
+        // exclusive scan of sz over the CTA
+        uint32_t incl = sz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, incl, d);
+            if ((int)lane >= d)
+                incl += t;
+        }
+        if (lane == 31)
+            warp_sum[wid] = incl;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < kEmitThreads / 32; ++w) {
+                const uint32_t t = warp_sum[w];
+                warp_sum[w] = run;
+                run += t;
+            }
+            warp_sum[kEmitThreads / 32] = run;
+        }
+        __syncthreads();
+        uint32_t o = carry + warp_sum[wid] + (incl - sz);
+        const uint32_t chunk_total = warp_sum[kEmitThreads / 32];
+        if (i < nr) {
+            if (lit) { // emit_literal :313-316
+                const uint32_t hdr = literal_header(lit, out + o);
+                const uint32_t src = p - lit;
+                if (lit >= kCoopLiteral) {
+                    const uint32_t slot = atomicAdd(&q_n, 1u);
+                    q_src[slot] = src, q_dst[slot] = o + hdr, q_len[slot] = lit;
+                } else {
+                    for (uint32_t k = 0; k < lit; ++k)
+                        out[o + hdr + k] = __ldg(b + src + k);
+                }
+                o += hdr + lit;
+            }
+            copy_emit(len, off, out + o); // emit_copy :323-329
+            if (i == nr - 1)
+                last_end = p + len;
+        }
+        __syncthreads();
+        const uint32_t nq = q_n;
+        for (uint32_t k = 0; k < nq; ++k)
+            coop_copy_ro(out + q_dst[k], b + q_src[k], q_len[k], tid, kEmitThreads);
+        carry += chunk_total;
+        __syncthreads();
+    }
+    // tail literal: exhaust_input :292-297 + emit_literal :401-402
+    if (nr) {
+        // last_end lives in the thread that handled record nr-1
+        __shared__ uint32_t s_last;
+        if ((nr - 1) % kEmitThreads == tid)
+            s_last = last_end;
+        __syncthreads();
+        last_end = s_last;
+    }
+    const uint32_t tail = n - last_end;
+    uint32_t hdr = 0;
+    if (tail) {
+        __shared__ uint32_t s_hdr;
+        if (tid == 0)
+            s_hdr = literal_header(tail, out + carry);
+        __syncthreads();
+        hdr = s_hdr;
+        coop_copy_ro(out + carry + hdr, b + last_end, tail, tid, kEmitThreads);
+    }
+    if (tid == 0)
+        sizes[blk] = carry + hdr + tail;
 }
 
 // ------------------------------------------------------------------------------- launchers
-static uint64_t g_launches_compress = 0;
-
 cudaError_t launch_compress(const uint8_t *d_in, uint64_t n_bytes, int mode, uint8_t *d_scratch, uint32_t *d_sizes,
-                            cudaStream_t st, uint64_t *launches)
+                            uint2 *d_recs, uint32_t *d_nrec, cudaStream_t st, uint64_t *launches)
 {
     const uint64_t nb = (n_bytes + kBlock - 1) / kBlock;
     if (nb == 0)
@@ -370,28 +462,31 @@ cudaError_t launch_compress(const uint8_t *d_in, uint64_t n_bytes, int mode, uin
         return cudaErrorInvalidValue;
     const dim3 grid((unsigned)nb), cta(32);
     if (mode == SNAPPY_B200_MODE_HASH) {
-        k_compress<0, 12, true><<<grid, cta, 4096 * 4, st>>>(d_in, n_bytes, d_scratch, d_sizes, 0);
+        k_parse<0, 12, true><<<grid, cta, 4096 * 4, st>>>(d_in, n_bytes, d_recs, d_nrec, 0);
         *launches += 1;
-        return cudaGetLastError();
+    } else {
+        // exact mode: 8 Ki slots (16 KiB), then 32 Ki slots (64 KiB), then 64 Ki slots (128 KiB)
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(k_parse<1, 15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (1 << 15) * 2);
+            if (e != cudaSuccess)
+                return e;
+            e = cudaFuncSetAttribute(k_parse<1, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 16) * 2);
+            if (e != cudaSuccess)
+                return e;
+            attr_done = true;
+        }
+        k_parse<1, 13, false><<<grid, cta, (1 << 13) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 0);
+        k_parse<1, 15, false><<<grid, cta, (1 << 15) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 1);
+        k_parse<1, 16, true><<<grid, cta, (1 << 16) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 1);
+        *launches += 3;
     }
-    // exact mode: 8 Ki slots (16 KiB), then 32 Ki slots (64 KiB), then 64 Ki slots (128 KiB)
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_compress<1, 15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (1 << 15) * 2);
-        if (e != cudaSuccess)
-            return e;
-        e = cudaFuncSetAttribute(k_compress<1, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 16) * 2);
-        if (e != cudaSuccess)
-            return e;
-        attr_done = true;
-    }
-    k_compress<1, 13, false><<<grid, cta, (1 << 13) * 2, st>>>(d_in, n_bytes, d_scratch, d_sizes, 0);
-    k_compress<1, 15, false><<<grid, cta, (1 << 15) * 2, st>>>(d_in, n_bytes, d_scratch, d_sizes, 1);
-    k_compress<1, 16, true><<<grid, cta, (1 << 16) * 2, st>>>(d_in, n_bytes, d_scratch, d_sizes, 1);
-    *launches += 3;
-    (void)g_launches_compress;
+    k_emit<<<grid, kEmitThreads, 0, st>>>(d_in, n_bytes, d_recs, d_nrec, d_scratch, d_sizes);
+    *launches += 1;
     return cudaGetLastError();
 }
+
+size_t compress_records_bytes(uint64_t n_blocks) { return n_blocks * (size_t)kMaxRecords * sizeof(uint2); }
 
 } // namespace sb200

@@ -26,7 +26,7 @@
 //                      per round.  Typical streams need 3-4 rounds; an adversarial one
 //                      degrades to sequential but stays correct.
 //   C  k_index_outlen  every live segment sums the output bytes of its elements
-//      k_scan_u64      exclusive scan -> output offset of every segment
+//      k_scan_*        exclusive scan -> output offset of every segment
 //   D  k_index_blocks  every live segment walks once more and records the stream offset of
 //                      each element that starts a 64 KiB output block; elements that straddle
 //                      a block boundary (legal raw Snappy, never produced by this framing) are
@@ -239,61 +239,109 @@ __global__ void __launch_bounds__(256) k_index_outlen(const uint8_t *__restrict_
     outlen[t] = sum;
 }
 
-// Exclusive scan of a u64 array by one CTA (the array has one entry per 128 stream bytes).
-__global__ void __launch_bounds__(1024) k_scan_u64(const uint64_t *__restrict__ in, uint64_t n,
-                                                   uint64_t *__restrict__ out, uint64_t *__restrict__ total)
+// Exclusive scan of a u64 array (one entry per 128 stream bytes, so millions of entries): tile
+// sums, a one-CTA scan of the tile sums, then a per-tile scan seeded with its tile offset.
+constexpr int kScanTile = 4096;   // elements per CTA
+constexpr int kScanCta = 512;     // threads per CTA, 8 elements each
+
+__device__ __forceinline__ uint64_t cta_exclusive_scan_u64(uint64_t v, uint64_t *warp_sum, uint64_t &total)
 {
-    constexpr int kItems = 8;
-    __shared__ uint64_t warp_sum[32];
-    __shared__ uint64_t carry_s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0)
-        carry_s = 0;
-    __syncthreads();
-    for (uint64_t start = 0; start < n; start += 1024ull * kItems) {
-        uint64_t v[kItems], sum = 0;
-        const uint64_t i0 = start + (uint64_t)tid * kItems;
+    uint64_t incl = v;
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) {
-            v[k] = i0 + k < n ? in[i0 + k] : 0;
-            sum += v[k];
-        }
-        uint64_t incl = sum;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t s = __shfl_up_sync(kFull, incl, d);
+        if ((int)lane >= d)
+            incl += s;
+    }
+    if (lane == 31)
+        warp_sum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t nw = blockDim.x >> 5;
+        const uint64_t w = lane < nw ? warp_sum[lane] : 0;
+        uint64_t wi = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint64_t s = __shfl_up_sync(kFull, incl, d);
+            const uint64_t s = __shfl_up_sync(kFull, wi, d);
             if ((int)lane >= d)
-                incl += s;
+                wi += s;
         }
-        if (lane == 31)
-            warp_sum[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            const uint64_t w = warp_sum[lane];
-            uint64_t wi = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint64_t s = __shfl_up_sync(kFull, wi, d);
-                if ((int)lane >= d)
-                    wi += s;
-            }
+        if (lane < nw)
             warp_sum[lane] = wi - w;
-        }
-        __syncthreads();
-        uint64_t run = carry_s + warp_sum[wid] + (incl - sum);
+        if (lane == 31)
+            warp_sum[32] = wi;
+    }
+    __syncthreads();
+    total = warp_sum[32];
+    const uint64_t r = warp_sum[wid] + (incl - v);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanCta) k_scan_tile_sums(const uint64_t *__restrict__ in, uint64_t n,
+                                                             uint64_t *__restrict__ tile_sums)
+{
+    __shared__ uint64_t warp_sum[33];
+    const uint64_t i0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * 8;
+    uint64_t sum = 0;
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) {
-            if (i0 + k < n)
-                out[i0 + k] = run;
+    for (int k = 0; k < 8; ++k)
+        sum += i0 + k < n ? in[i0 + k] : 0;
+    uint64_t total;
+    (void)cta_exclusive_scan_u64(sum, warp_sum, total);
+    if (threadIdx.x == 0)
+        tile_sums[blockIdx.x] = total;
+}
+
+// One CTA: exclusive scan of the tile sums in place (loops when there are more than 4096).
+__global__ void __launch_bounds__(kScanCta) k_scan_tiles(uint64_t *__restrict__ tile_sums, uint64_t n_tiles,
+                                                         uint64_t *__restrict__ total_out)
+{
+    __shared__ uint64_t warp_sum[33];
+    uint64_t carry = 0;
+    for (uint64_t start = 0; start < n_tiles; start += kScanTile) {
+        const uint64_t i0 = start + (uint64_t)threadIdx.x * 8;
+        uint64_t v[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = i0 + k < n_tiles ? tile_sums[i0 + k] : 0;
+            sum += v[k];
+        }
+        uint64_t total;
+        uint64_t run = carry + cta_exclusive_scan_u64(sum, warp_sum, total);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (i0 + k < n_tiles)
+                tile_sums[i0 + k] = run;
             run += v[k];
         }
-        __syncthreads();
-        if (tid == 1023)
-            carry_s = run;
-        __syncthreads();
+        carry += total;
     }
-    if (tid == 0)
-        *total = carry_s;
+    if (threadIdx.x == 0)
+        *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanCta) k_scan_apply(const uint64_t *__restrict__ in, uint64_t n,
+                                                         const uint64_t *__restrict__ tile_offsets,
+                                                         uint64_t *__restrict__ out)
+{
+    __shared__ uint64_t warp_sum[33];
+    const uint64_t i0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * 8;
+    uint64_t v[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        v[k] = i0 + k < n ? in[i0 + k] : 0;
+        sum += v[k];
+    }
+    uint64_t total;
+    uint64_t run = tile_offsets[blockIdx.x] + cta_exclusive_scan_u64(sum, warp_sum, total);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (i0 + k < n)
+            out[i0 + k] = run;
+        run += v[k];
+    }
 }
 
 // D: stream offset of the element that opens each 64 KiB output block.
@@ -353,6 +401,7 @@ struct IndexWorkspace {
     uint64_t *outlen;
     uint64_t *outoff;
     uint64_t *total;
+    uint64_t *tile_sums;
     uint32_t *changed;
     uint8_t *entry;
 };
@@ -362,7 +411,9 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 size_t index_workspace_bytes(uint64_t stream_bytes)
 {
     const uint64_t nseg = (stream_bytes + kSeg - 1) / kSeg + 1;
-    return align_up(nseg * 16, 256) + 4 * align_up(nseg * 8, 256) + 256 + 256 + align_up(nseg, 256) + 256;
+    const uint64_t ntile = (nseg + kScanTile - 1) / kScanTile + 1;
+    return align_up(nseg * 16, 256) + 4 * align_up(nseg * 8, 256) + align_up(ntile * 8, 256) + 256 + 256 +
+           align_up(nseg, 256) + 256;
 }
 
 static IndexWorkspace carve(void *ws, uint64_t stream_bytes)
@@ -376,6 +427,7 @@ static IndexWorkspace carve(void *ws, uint64_t stream_bytes)
     w.outlen = reinterpret_cast<uint64_t *>(p), p += align_up(nseg * 8, 256);
     w.outoff = reinterpret_cast<uint64_t *>(p), p += align_up(nseg * 8, 256);
     w.total = reinterpret_cast<uint64_t *>(p), p += 256;
+    w.tile_sums = reinterpret_cast<uint64_t *>(p), p += align_up(((nseg + kScanTile - 1) / kScanTile + 1) * 8, 256);
     w.changed = reinterpret_cast<uint32_t *>(p), p += 256;
     w.entry = p;
     return w;
@@ -433,11 +485,14 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
         }
     }
     k_index_outlen<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outlen, d_status);
-    k_scan_u64<<<1, 1024, 0, st>>>(w.outlen, nseg, w.outoff, w.total);
+    const uint64_t ntile = (nseg + kScanTile - 1) / kScanTile;
+    k_scan_tile_sums<<<(unsigned)ntile, kScanCta, 0, st>>>(w.outlen, nseg, w.tile_sums);
+    k_scan_tiles<<<1, kScanCta, 0, st>>>(w.tile_sums, ntile, w.total);
+    k_scan_apply<<<(unsigned)ntile, kScanCta, 0, st>>>(w.outlen, nseg, w.tile_sums, w.outoff);
     k_index_blocks<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outoff, body_offset, n_blocks,
                                          d_block_offsets, d_status);
     k_index_finish<<<1, 32, 0, st>>>(w.total, total_out, stream_bytes, n_blocks, d_block_offsets, d_status);
-    *launches += 4;
+    *launches += 6;
     return cudaGetLastError();
 }
 
