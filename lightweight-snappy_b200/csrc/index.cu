@@ -11,20 +11,27 @@
 //                      and the offset at which it leaves the segment.  Snappy streams
 //                      re-synchronise within a few elements, so most of these walks merge
 //                      into the true element chain long before the segment ends.
-//   B  k_index_scatter / k_index_apply   relaxation rounds.  Every segment publishes the exit
-//                      of its current walk to the segment it lands in, and a live segment marks
-//                      the segments a long literal jumps over as "dead" (holding no element
-//                      start).  A segment that was itself marked dead keeps publishing its exit,
-//                      but at low priority; among equal priorities the lowest source wins.  A segment
-//                      whose entry changed re-walks from the new entry until it meets its old
-//                      path.  Segment 0's entry is known, every other segment is claimed or
-//                      marked by a live predecessor, so the beliefs are correct on a prefix
-//                      that grows every round, and a round that changes nothing is the unique
-//                      fixed point = the true chain.  Keeping dead segments talking matters:
-//                      when a mis-speculated "long literal" wrongly kills a run of segments,
-//                      they all come back in the round after it is corrected instead of one
-//                      per round.  Typical streams need 3-4 rounds; an adversarial one
-//                      degrades to sequential but stays correct.
+//   A' k_index_link    the exit of segment t-1 is walked into segment t until it meets t's path,
+//                      and those offsets are added to the path
+//   B  k_group_*       the segments are taken 64 at a time (8 KiB "groups"), one thread per
+//                      group.  A group's walk is a chase through its segments: where the chain
+//                      enters a segment on that segment's recorded path the segment's exit is
+//                      taken as is, otherwise the tags are walked until the path is met.  Groups
+//                      are then resolved by relaxation rounds (k_group_scatter / k_group_apply):
+//                      every group publishes the exit of its current chase to the group it lands
+//                      in, and a live group marks the groups a long literal jumps over as "dead"
+//                      (holding no element start).  A group that was itself marked dead keeps
+//                      publishing its exit, but at low priority; among equal priorities the
+//                      lowest source wins.  A group whose entry changed re-chases from the new
+//                      entry unless that entry lies on its old chain.  Group 0's entry is known,
+//                      every other group is claimed or marked by a live predecessor, so the
+//                      beliefs are correct on a prefix that grows every round, and a round that
+//                      changes nothing is the unique fixed point = the true chain.  Keeping dead
+//                      groups talking matters: when a mis-speculated "long literal" wrongly
+//                      kills a run of groups they all come back in the round after it is
+//                      corrected instead of one per round.  An adversarial stream degrades to
+//                      sequential but stays correct.  k_group_final then chases every live group
+//                      once more from its true entry and records the entry of each segment.
 //   C  k_index_outlen  every live segment sums the output bytes of its elements
 //      k_scan_*        exclusive scan -> output offset of every segment
 //   D  k_index_blocks  every live segment walks once more and records the stream offset of
@@ -119,8 +126,7 @@ __device__ __forceinline__ uint64_t walk(const uint8_t *__restrict__ body, uint6
 }
 
 __global__ void __launch_bounds__(256) k_index_spec(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
-                                                    uint4 *__restrict__ paths, uint64_t *__restrict__ exits,
-                                                    uint8_t *__restrict__ entry)
+                                                    uint4 *__restrict__ paths, uint64_t *__restrict__ exits)
 {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t >= nseg)
@@ -133,82 +139,286 @@ __global__ void __launch_bounds__(256) k_index_spec(const uint8_t *__restrict__ 
     const uint64_t x = walk(body, body_len, lo, hi, lo, nullptr, p, merged);
     paths[t] = make_uint4(p.bits[0], p.bits[1], p.bits[2], p.bits[3]);
     exits[t] = x;
-    entry[t] = 0; // everybody starts out believing an element begins at its first byte
 }
 
-__global__ void __launch_bounds__(256) k_index_scatter(uint64_t body_len, uint64_t nseg,
-                                                       const uint64_t *__restrict__ exits,
-                                                       const uint8_t *__restrict__ entry,
-                                                       unsigned long long *__restrict__ claim)
+// A': where the walk of segment t-1 lands in segment t, that offset is (in converged regions)
+// the true entry of t, but it usually lies before the point where t's own speculative walk
+// merged into the chain.  Walk from it until t's path is met and add those offsets to the
+// path, so that the group chase below finds the chain "on path" in every such segment.
+__global__ void __launch_bounds__(256) k_index_link(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
+                                                    uint4 *__restrict__ paths, const uint64_t *__restrict__ exits)
 {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (t >= nseg)
+    if (t == 0 || t >= nseg)
         return;
-    const bool dead = entry[t] & kDead;
-    const unsigned long long prio = dead ? kLowPrio : 0ull;
-    const uint64_t x = exits[t];
-    const uint64_t u = x / kSeg; // segment the chain lands in
-    if (!dead) {
-        // Segments jumped over hold no element start (only a live source may say so: a dead
-        // segment's walk is pure speculation, and its bogus "huge literals" would otherwise keep
-        // killing true segments round after round).  An element of this framing never spans
-        // more than one 64 KiB block (+ header), which bounds the work a mis-speculated literal
-        // can cause; a true element that long is reported as SNAPPY_B200_ST_FRAMING by
-        // k_index_outlen.
-        const uint64_t vmax = min(min(u, nseg), t + 1 + (kBlock + 1024) / kSeg);
-        for (uint64_t v = t + 1; v < vmax; ++v)
-            atomicMin(claim + v, (unsigned long long)((t << 8) | kMark));
-        if (u < nseg && x >= body_len) // the chain ends inside the last segment: nothing starts there
-            atomicMin(claim + u, (unsigned long long)((t << 8) | kMark));
+    const uint64_t x = exits[t - 1];
+    const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
+    if (x < lo || x >= hi)
+        return;
+    const uint4 pv = paths[t];
+    Path p;
+    p.bits[0] = pv.x, p.bits[1] = pv.y, p.bits[2] = pv.z, p.bits[3] = pv.w;
+    if (p.test((uint32_t)(x - lo)))
+        return;
+    Path fresh;
+    fresh.clear();
+    bool merged;
+    (void)walk(body, body_len, lo, hi, x, &p, fresh, merged);
+    if (merged)
+        paths[t] = make_uint4(p.bits[0] | fresh.bits[0], p.bits[1] | fresh.bits[1], p.bits[2] | fresh.bits[2],
+                              p.bits[3] | fresh.bits[3]);
+}
+
+// ---- groups of kGroup segments ------------------------------------------------------------
+constexpr uint32_t kGroup = 64;                   // segments per group
+constexpr uint64_t kGroupBytes = kGroup * kSeg;   // 8 KiB of stream
+constexpr uint32_t kGDead = 0x80000000u;          // g_entry bit 31: no element starts in this group
+constexpr uint32_t kGMark = 0xffffffu;            // claim payload: "a literal jumps over you"
+
+// One warp works on one group.  The group's per-segment records (path map + exit) are staged
+// in shared memory with coalesced loads; the chase itself is a short dependent chain that all
+// lanes execute redundantly on the staged copy.
+constexpr int kGroupCta = 128;                 // 4 warps = 4 groups per CTA
+struct GroupStage {
+    uint4 paths[kGroup];
+    uint64_t exits[kGroup];
+    uint8_t entry[kGroup];
+};
+
+__device__ __forceinline__ void group_stage(GroupStage &sm, uint64_t g, uint64_t nseg,
+                                            const uint4 *__restrict__ paths, const uint64_t *__restrict__ exits)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t s0 = g * kGroup;
+#pragma unroll
+    for (uint32_t k = lane; k < kGroup; k += 32) {
+        const bool ok = s0 + k < nseg;
+        sm.paths[k] = ok ? paths[s0 + k] : make_uint4(0, 0, 0, 0);
+        sm.exits[k] = ok ? exits[s0 + k] : 0;
     }
-    if (u < nseg && x < body_len)
-        atomicMin(claim + u, prio | (unsigned long long)((t << 8) | (x - u * kSeg)));
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(256) k_index_apply(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
-                                                     uint4 *__restrict__ paths, uint64_t *__restrict__ exits,
-                                                     uint8_t *__restrict__ entry,
-                                                     unsigned long long *__restrict__ claim,
-                                                     uint32_t *__restrict__ changed)
+// Chases the element chain from body offset e to the end of group g (warp-uniform).  vis gets
+// one bit per segment that the chain entered on that segment's recorded path (from such a
+// point on the chain is the recorded one).  When record is set, the entry of every segment is
+// left in sm.entry (kDead for segments the chain jumps over).
+__device__ __forceinline__ uint64_t group_chase(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
+                                                GroupStage &sm, uint64_t g, uint64_t e, uint64_t &vis, bool record)
 {
-    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (t >= nseg)
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t s0 = g * kGroup;
+    const uint64_t s1 = min(s0 + kGroup, nseg);
+    const uint64_t g_hi = min(s1 * kSeg, body_len);
+    vis = 0;
+    if (record) {
+        sm.entry[lane] = (uint8_t)kDead;
+        sm.entry[lane + 32] = (uint8_t)kDead;
+        __syncwarp();
+    }
+    while (e < g_hi) {
+        const uint64_t sg = e / kSeg;
+        const uint32_t k = (uint32_t)(sg - s0);
+        const uint32_t rel = (uint32_t)(e - sg * kSeg);
+        if (record && lane == 0)
+            sm.entry[k] = (uint8_t)rel;
+        const uint4 pv = sm.paths[k];
+        Path p;
+        p.bits[0] = pv.x, p.bits[1] = pv.y, p.bits[2] = pv.z, p.bits[3] = pv.w;
+        if (p.test(rel)) {
+            vis |= 1ull << k;
+            e = sm.exits[k];
+        } else {
+            Path fresh;
+            fresh.clear();
+            bool merged;
+            const uint64_t lo = sg * kSeg, hi = min(lo + kSeg, body_len);
+            const uint64_t x = walk(body, body_len, lo, hi, e, &p, fresh, merged);
+            if (merged) {
+                vis |= 1ull << k;
+                e = sm.exits[k];
+            } else {
+                e = x;
+            }
+        }
+    }
+    __syncwarp();
+    return e;
+}
+
+// Initial state: every group believes an element starts at its first byte.
+__global__ void __launch_bounds__(kGroupCta) k_group_init(const uint8_t *__restrict__ body, uint64_t body_len,
+                                                          uint64_t nseg, uint64_t ngroup,
+                                                          const uint4 *__restrict__ paths,
+                                                          const uint64_t *__restrict__ exits,
+                                                          uint32_t *__restrict__ g_entry, uint64_t *__restrict__ g_exit,
+                                                          uint64_t *__restrict__ g_vis,
+                                                          unsigned long long *__restrict__ g_claim)
+{
+    __shared__ GroupStage stage[kGroupCta / 32];
+    const uint64_t g = blockIdx.x * (uint64_t)(kGroupCta / 32) + (threadIdx.x >> 5);
+    if (g >= ngroup)
         return;
-    const unsigned long long c = claim[t];
-    claim[t] = kNone; // ready for the next round
-    const uint32_t old = entry[t];
-    const uint32_t payload = (uint32_t)(c & 0xffu);
+    GroupStage &sm = stage[threadIdx.x >> 5];
+    group_stage(sm, g, nseg, paths, exits);
+    uint64_t vis;
+    const uint64_t x = group_chase(body, body_len, nseg, sm, g, g * kGroupBytes, vis, false);
+    if ((threadIdx.x & 31) == 0) {
+        g_exit[g] = x;
+        g_vis[g] = vis;
+        g_entry[g] = 0;
+        g_claim[g] = kNone;
+    }
+}
+
+// Runs of incompressible 64 KiB blocks are chains of maximal literals, "f4 ff ff" + 65536 bytes,
+// each of which can only be found through the one before: one hop per round.  When a live
+// group's chain leaves through such a literal, the positions of the next kLookahead headers are
+// guessed (65539 apart), fetched all at once, and the confirmed prefix of the run is published
+// in the same round.
+constexpr uint32_t kLookahead = 24;
+constexpr uint64_t kMaxLiteralElem = 3 + (uint64_t)kBlock; // header + payload of a maximal literal
+
+__device__ __forceinline__ bool is_max_literal(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t q)
+{
+    return q + kMaxLiteralElem <= body_len && __ldg(body + q) == 0xf4 && __ldg(body + q + 1) == 0xff &&
+           __ldg(body + q + 2) == 0xff;
+}
+
+__global__ void __launch_bounds__(128) k_group_scatter(const uint8_t *__restrict__ body, uint64_t body_len,
+                                                       uint64_t ngroup, const uint32_t *__restrict__ g_entry,
+                                                       const uint64_t *__restrict__ g_exit,
+                                                       unsigned long long *__restrict__ g_claim)
+{
+    const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g >= ngroup)
+        return;
+    const bool dead = g_entry[g] & kGDead;
+    const unsigned long long prio = dead ? kLowPrio : 0ull;
+    const uint64_t x = g_exit[g];
+    const uint64_t u = x / kGroupBytes; // group the chain lands in
+    if (!dead) {
+        // Groups jumped over hold no element start (only a live source may say so: a dead
+        // group's chase is pure speculation).  An element of this framing never spans more than
+        // one 64 KiB block (+ header), which bounds the work a mis-speculated literal can cause;
+        // a true element that long is reported as SNAPPY_B200_ST_FRAMING by k_index_outlen.
+        const uint64_t vmax = min(min(u, ngroup), g + 2 + (kBlock + 1024) / kGroupBytes);
+        for (uint64_t v = g + 1; v < vmax; ++v)
+            atomicMin(g_claim + v, (unsigned long long)((g << 24) | kGMark));
+        if (u < ngroup && x >= body_len) // the chain ends inside the last group: nothing starts there
+            atomicMin(g_claim + u, (unsigned long long)((g << 24) | kGMark));
+    }
+    if (u < ngroup && x < body_len)
+        atomicMin(g_claim + u, prio | (unsigned long long)((g << 24) | (x - u * kGroupBytes)));
+    if (!dead && u > g + 1 && x < body_len) {
+        // left through a long literal: look ahead along a possible run of maximal literals
+        bool ok[kLookahead];
+#pragma unroll
+        for (uint32_t k = 0; k < kLookahead; ++k)
+            ok[k] = is_max_literal(body, body_len, x + k * kMaxLiteralElem);
+        uint64_t q = x;
+#pragma unroll
+        for (uint32_t k = 0; k < kLookahead; ++k) {
+            if (!ok[k])
+                break;
+            // the element at q is a maximal literal: the chain continues at q + 65539
+            const uint64_t qn = q + kMaxLiteralElem;
+            const uint64_t uq = q / kGroupBytes, un = qn / kGroupBytes;
+            for (uint64_t v = uq + 1; v < un && v < ngroup; ++v)
+                atomicMin(g_claim + v, (unsigned long long)((g << 24) | kGMark));
+            if (un < ngroup) {
+                if (qn < body_len)
+                    atomicMin(g_claim + un, (unsigned long long)((g << 24) | (qn - un * kGroupBytes)));
+                else
+                    atomicMin(g_claim + un, (unsigned long long)((g << 24) | kGMark));
+            }
+            q = qn;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kGroupCta) k_group_apply(const uint8_t *__restrict__ body, uint64_t body_len,
+                                                           uint64_t nseg, uint64_t ngroup,
+                                                           const uint4 *__restrict__ paths,
+                                                           const uint64_t *__restrict__ exits,
+                                                           uint32_t *__restrict__ g_entry,
+                                                           uint64_t *__restrict__ g_exit, uint64_t *__restrict__ g_vis,
+                                                           unsigned long long *__restrict__ g_claim,
+                                                           uint32_t *__restrict__ changed)
+{
+    __shared__ GroupStage stage[kGroupCta / 32];
+    const uint64_t g = blockIdx.x * (uint64_t)(kGroupCta / 32) + (threadIdx.x >> 5);
+    if (g >= ngroup)
+        return;
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned long long c = g_claim[g]; // every lane reads the same words (broadcast)
+    const uint32_t old = g_entry[g];
+    __syncwarp();
+    if (lane == 0)
+        g_claim[g] = kNone; // ready for the next round
+    const uint32_t payload = (uint32_t)(c & 0xffffffu);
     uint32_t ne;
-    if (t == 0)
+    if (g == 0)
         ne = 0; // the body starts with an element
-    else if (c == kNone || payload == kMark)
-        ne = (old & 0x7fu) | kDead;
+    else if (c == kNone || payload == kGMark)
+        ne = (old & ~kGDead) | kGDead;
     else
         ne = payload;
     if (ne == old)
         return;
-    entry[t] = (uint8_t)ne;
-    atomicOr(changed, 1u);
-    if ((ne & kDead) || (ne & 0x7fu) == (old & 0x7fu))
-        return; // dead, or revived with the entry it already walked from
-    const uint64_t lo = t * kSeg;
-    const uint64_t hi = min(lo + kSeg, body_len);
-    const uint4 pv = paths[t];
+    if (lane == 0) {
+        g_entry[g] = ne;
+        atomicOr(changed, 1u);
+    }
+    if ((ne & kGDead) || ne == (old & ~kGDead))
+        return; // dead, or revived with the entry it already chased from
+    // does the new entry lie on the old chain?  (it does if the old chain entered that segment on
+    // the segment's recorded path and the new entry is on that path too)
+    const uint64_t e = g * kGroupBytes + ne;
+    const uint64_t sg = e / kSeg;
+    const uint4 pv = paths[sg];
     Path p;
     p.bits[0] = pv.x, p.bits[1] = pv.y, p.bits[2] = pv.z, p.bits[3] = pv.w;
-    Path fresh;
-    fresh.clear();
-    bool merged;
-    const uint64_t x = walk(body, body_len, lo, hi, lo + ne, &p, fresh, merged);
-    if (merged) {
-        // rejoined the old path: the old exit stands, and every offset of either walk leads to it
-#pragma unroll
-        for (int w = 0; w < 4; ++w)
-            fresh.bits[w] |= p.bits[w];
-    } else {
-        exits[t] = x; // a different chain: only its own offsets are known to lead to x
+    if (((g_vis[g] >> (sg - g * kGroup)) & 1ull) && p.test((uint32_t)(e - sg * kSeg)))
+        return; // same exit, and everything the old chain recorded still holds from here on
+    GroupStage &sm = stage[threadIdx.x >> 5];
+    group_stage(sm, g, nseg, paths, exits);
+    uint64_t vis;
+    const uint64_t x = group_chase(body, body_len, nseg, sm, g, e, vis, false);
+    if (lane == 0) {
+        g_exit[g] = x;
+        g_vis[g] = vis;
     }
-    paths[t] = make_uint4(fresh.bits[0], fresh.bits[1], fresh.bits[2], fresh.bits[3]);
+}
+
+__global__ void __launch_bounds__(kGroupCta) k_group_final(const uint8_t *__restrict__ body, uint64_t body_len,
+                                                           uint64_t nseg, uint64_t ngroup,
+                                                           const uint4 *__restrict__ paths,
+                                                           const uint64_t *__restrict__ exits,
+                                                           const uint32_t *__restrict__ g_entry,
+                                                           uint8_t *__restrict__ entry)
+{
+    __shared__ GroupStage stage[kGroupCta / 32];
+    const uint64_t g = blockIdx.x * (uint64_t)(kGroupCta / 32) + (threadIdx.x >> 5);
+    if (g >= ngroup)
+        return;
+    const uint32_t lane = threadIdx.x & 31;
+    GroupStage &sm = stage[threadIdx.x >> 5];
+    const uint32_t ge = g_entry[g];
+    if (ge & kGDead) {
+        sm.entry[lane] = (uint8_t)kDead;
+        sm.entry[lane + 32] = (uint8_t)kDead;
+        __syncwarp();
+    } else {
+        group_stage(sm, g, nseg, paths, exits);
+        uint64_t vis;
+        (void)group_chase(body, body_len, nseg, sm, g, g * kGroupBytes + ge, vis, true);
+    }
+    const uint64_t s0 = g * kGroup;
+    if (s0 + lane < nseg)
+        entry[s0 + lane] = sm.entry[lane];
+    if (s0 + lane + 32 < nseg)
+        entry[s0 + lane + 32] = sm.entry[lane + 32];
 }
 
 // C: output bytes produced by the elements that start in each live segment.
@@ -404,6 +614,9 @@ struct IndexWorkspace {
     uint64_t *tile_sums;
     uint32_t *changed;
     uint8_t *entry;
+    uint32_t *g_entry;
+    uint64_t *g_exit;
+    uint64_t *g_vis;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -412,8 +625,9 @@ size_t index_workspace_bytes(uint64_t stream_bytes)
 {
     const uint64_t nseg = (stream_bytes + kSeg - 1) / kSeg + 1;
     const uint64_t ntile = (nseg + kScanTile - 1) / kScanTile + 1;
+    const uint64_t ngroup = (nseg + kGroup - 1) / kGroup + 1;
     return align_up(nseg * 16, 256) + 4 * align_up(nseg * 8, 256) + align_up(ntile * 8, 256) + 256 + 256 +
-           align_up(nseg, 256) + 256;
+           align_up(nseg, 256) + align_up(ngroup * 4, 256) + 2 * align_up(ngroup * 8, 256) + 256;
 }
 
 static IndexWorkspace carve(void *ws, uint64_t stream_bytes)
@@ -428,8 +642,12 @@ static IndexWorkspace carve(void *ws, uint64_t stream_bytes)
     w.outoff = reinterpret_cast<uint64_t *>(p), p += align_up(nseg * 8, 256);
     w.total = reinterpret_cast<uint64_t *>(p), p += 256;
     w.tile_sums = reinterpret_cast<uint64_t *>(p), p += align_up(((nseg + kScanTile - 1) / kScanTile + 1) * 8, 256);
-    w.changed = reinterpret_cast<uint32_t *>(p), p += 256;
-    w.entry = p;
+    w.changed = reinterpret_cast<uint32_t *>(p), p += 256; // 64 round flags
+    w.entry = p, p += align_up(nseg, 256);
+    const uint64_t ngroup = (nseg + kGroup - 1) / kGroup + 1;
+    w.g_entry = reinterpret_cast<uint32_t *>(p), p += align_up(ngroup * 4, 256);
+    w.g_exit = reinterpret_cast<uint64_t *>(p), p += align_up(ngroup * 8, 256);
+    w.g_vis = reinterpret_cast<uint64_t *>(p);
     return w;
 }
 
@@ -453,30 +671,36 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
         return cudaGetLastError();
     }
     const unsigned grid = (unsigned)((nseg + 255) / 256);
-    k_fill_u64<<<grid, 256, 0, st>>>(w.claim, nseg, kNone);
-    k_index_spec<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits, w.entry);
-    *launches += 2;
-    // The "did anything change" flag is only read back every kCheck rounds: a round costs two
-    // short kernels, a host round trip costs more.
-    constexpr uint64_t kCheck = 4;
-    const uint64_t max_rounds = nseg + 2 + kCheck;
-    if ((e = cudaMemsetAsync(w.changed, 0, 4 * kCheck, st)) != cudaSuccess)
+    const uint64_t ngroup = (nseg + kGroup - 1) / kGroup;
+    const unsigned ggrid = (unsigned)((ngroup + 127) / 128);                       // one thread per group
+    const unsigned wgrid = (unsigned)((ngroup + kGroupCta / 32 - 1) / (kGroupCta / 32)); // one warp per group
+    k_index_spec<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits);
+    k_index_link<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits);
+    k_group_init<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.g_exit, w.g_vis,
+                                        w.claim);
+    *launches += 3;
+    // The "did anything change" flags are only read back every few rounds (4, then 8, 16, ... 64):
+    // a round costs two short kernels, a host round trip costs more.
+    constexpr uint32_t kMaxBatch = 64;
+    const uint64_t max_rounds = ngroup + 2 + kMaxBatch;
+    if ((e = cudaMemsetAsync(w.changed, 0, 4 * kMaxBatch, st)) != cudaSuccess)
         return e;
-    for (uint64_t round = 0; round < max_rounds; round += kCheck) {
-        for (uint64_t k = 0; k < kCheck; ++k) {
-            k_index_scatter<<<grid, 256, 0, st>>>(body_len, nseg, w.exits, w.entry, w.claim);
-            k_index_apply<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits, w.entry, w.claim,
-                                                w.changed + k);
+    uint32_t batch = 4;
+    for (uint64_t round = 0; round < max_rounds; round += batch, batch = min(batch * 2, kMaxBatch)) {
+        for (uint32_t k = 0; k < batch; ++k) {
+            k_group_scatter<<<ggrid, 128, 0, st>>>(body, body_len, ngroup, w.g_entry, w.g_exit, w.claim);
+            k_group_apply<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry,
+                                                       w.g_exit, w.g_vis, w.claim, w.changed + k);
         }
-        *launches += 2 * kCheck;
-        uint32_t changed[kCheck];
-        if ((e = cudaMemcpyAsync(changed, w.changed, 4 * kCheck, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-            (e = cudaMemsetAsync(w.changed, 0, 4 * kCheck, st)) != cudaSuccess ||
+        *launches += 2 * batch;
+        uint32_t changed[kMaxBatch];
+        if ((e = cudaMemcpyAsync(changed, w.changed, 4 * batch, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+            (e = cudaMemsetAsync(w.changed, 0, 4 * kMaxBatch, st)) != cudaSuccess ||
             (e = cudaStreamSynchronize(st)) != cudaSuccess)
             return e;
-        g_last_rounds = round + kCheck;
-        if (!changed[kCheck - 1]) { // a round without change is the fixed point
-            for (uint64_t k = 0; k < kCheck; ++k)
+        g_last_rounds = round + batch;
+        if (!changed[batch - 1]) { // a round without change is the fixed point
+            for (uint32_t k = 0; k < batch; ++k)
                 if (!changed[k]) {
                     g_last_rounds = round + k + 1;
                     break;
@@ -484,6 +708,8 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
             break;
         }
     }
+    k_group_final<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.entry);
+    *launches += 1;
     k_index_outlen<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outlen, d_status);
     const uint64_t ntile = (nseg + kScanTile - 1) / kScanTile;
     k_scan_tile_sums<<<(unsigned)ntile, kScanCta, 0, st>>>(w.outlen, nseg, w.tile_sums);

@@ -7,6 +7,8 @@ from oracle_lib import Oracle
 
 NO_DEAD_MARKS = int(os.environ.get('NDM', '1'))
 SEG = 128; DEAD = 0x80; MARK = 0xff; NONE = (1 << 64) - 1; LOW = 1 << 63
+RULE = int(os.environ.get('RULE', '1'))
+C_MARK, C_PROP, C_DEAD = (0, 1 << 61, 2 << 61) if RULE else (0, 0, 1 << 63)
 
 def decode_at(body, e):
     n = len(body); tag = body[e]; typ = tag & 3
@@ -43,14 +45,13 @@ def run(body, verbose=False):
         rounds += 1
         claim = [NONE] * nseg
         for t in range(nseg):
-            prio = LOW if entry[t] & DEAD else 0
+            dead = entry[t] & DEAD
             x = exits[t]; u = x // SEG
-            vmax = min(min(u, nseg), t + 1 + (65536 + 1024) // SEG)
-            if not prio or not NO_DEAD_MARKS:
-                for v in range(t + 1, vmax): claim[v] = min(claim[v], prio | (t << 8) | MARK)
-            if u < nseg:
-                if x < n: claim[u] = min(claim[u], prio | (t << 8) | (x - u * SEG))
-                elif not prio or not NO_DEAD_MARKS: claim[u] = min(claim[u], prio | (t << 8) | MARK)
+            if not dead:
+                vmax = min(min(u, nseg), t + 1 + (65536 + 1024) // SEG)
+                for v in range(t + 1, vmax): claim[v] = min(claim[v], C_MARK | (t << 8) | MARK)
+                if u < nseg and x >= n: claim[u] = min(claim[u], C_MARK | (t << 8) | MARK)
+            if u < nseg and x < n: claim[u] = min(claim[u], (C_DEAD if dead else C_PROP) | (t << 8) | (x - u * SEG))
         changed = 0; nch = 0
         for t in range(nseg):
             c = claim[t]; old = entry[t]; payload = c & 0xff
