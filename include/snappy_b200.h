@@ -16,7 +16,7 @@
  *        src/snappy_compression.c:384-403 driven by snappy_compress :414-428
  *   snappy_b200_compress_device / _host, MODE_BST  -> src/snappy_compression_tree.c:269-288
  *        driven by snappy_compress_bst :291-306 (exact-key dictionary of src/BST.c)
- *   snappy_b200_decompress_device* / _host          -> src/snappy_decompression.c:345-363
+ *   snappy_b200_decompress_device[_indexed] / _host -> src/snappy_decompression.c:345-363
  *        (element loop :290-333, literal :193-239, copy :253-280)
  *   snappy_b200_index_device                        -> the block boundaries that the
  *        sequential loop at src/snappy_decompression.c:353-356 discovers implicitly
@@ -106,6 +106,22 @@ size_t snappy_b200_index_workspace_bytes(uint64_t stream_bytes);
 int snappy_b200_index_device(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
                              uint64_t total_out, uint64_t *d_block_offsets, uint32_t *d_status,
                              void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* The segment-driven decoder on its own: requires the workspace exactly as
+ * snappy_b200_index_device left it for this stream (it holds the element maps) and the
+ * block offsets that call produced.                                                      */
+int snappy_b200_decode_segments_device(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
+                                       uint64_t total_out, uint8_t *d_out, const uint64_t *d_block_offsets,
+                                       uint32_t *d_status, void *d_workspace, size_t workspace_bytes,
+                                       void *stream);
+
+/* Decodes an index-less stream: snappy_b200_index_device followed by the segment-driven
+ * decoder, which uses the element maps K0 leaves in the workspace.  d_block_offsets
+ * [n_blocks+1] is filled as a by-product.  Workspace: snappy_b200_index_workspace_bytes.
+ * Synchronises the stream between K0 rounds; the decode itself is only enqueued.           */
+int snappy_b200_decompress_device(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
+                                  uint64_t total_out, uint8_t *d_out, uint64_t *d_block_offsets,
+                                  uint32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------- 2. host-buffer API
  * Synchronous.  Host pointers (pageable or pinned); staging through pinned buffers and

@@ -47,6 +47,10 @@ SIGNATURES = {
     "snappy_b200_index_workspace_bytes": (C.c_size_t, [C.c_uint64]),
     "snappy_b200_index_device": (C.c_int, [_u8p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u8p, _u8p, C.c_size_t,
                                            C.c_void_p]),
+    "snappy_b200_decode_segments_device": (C.c_int, [_u8p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u8p, _u8p, _u8p,
+                                                     C.c_size_t, C.c_void_p]),
+    "snappy_b200_decompress_device": (C.c_int, [_u8p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u8p, _u8p, _u8p,
+                                                C.c_size_t, C.c_void_p]),
     "snappy_b200_compress_host": (C.c_int, [_u8p, C.c_uint64, C.c_int, _u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "snappy_b200_uncompressed_length": (C.c_int, [_u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "snappy_b200_decompress_host": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
@@ -200,6 +204,22 @@ class DeviceCodec:
         _check(lib().snappy_b200_decompress_device_indexed(
             stream_t.data_ptr(), block_offsets.data_ptr(), block_count(total_out), total_out, out.data_ptr(),
             self.status.data_ptr(), self._stream()))
+
+    def decompress(self, stream_t, stream_bytes: int, body_offset: int, total_out: int, out, block_offsets=None):
+        """Index-less decode: K0 + segment-driven decoder (synchronises between K0 rounds)."""
+        if block_offsets is None:
+            block_offsets = self.block_offsets
+        self.status.zero_()
+        _check(lib().snappy_b200_decompress_device(
+            stream_t.data_ptr(), stream_bytes, body_offset, total_out, out.data_ptr(), block_offsets.data_ptr(),
+            self.status.data_ptr(), self.workspace.data_ptr(), self.workspace.numel(), self._stream()))
+        return block_offsets
+
+    def decode_segments(self, stream_t, stream_bytes: int, body_offset: int, total_out: int, out, block_offsets):
+        """Second half of decompress(): needs the workspace as index() left it (status is kept)."""
+        _check(lib().snappy_b200_decode_segments_device(
+            stream_t.data_ptr(), stream_bytes, body_offset, total_out, out.data_ptr(), block_offsets.data_ptr(),
+            self.status.data_ptr(), self.workspace.data_ptr(), self.workspace.numel(), self._stream()))
 
     def index(self, stream_t, stream_bytes: int, body_offset: int, total_out: int, block_offsets=None):
         """K0: block boundaries of an index-less stream (synchronises between rounds)."""

@@ -16,6 +16,9 @@ cudaError_t launch_compact(const uint8_t *, const uint32_t *, uint64_t, uint64_t
                            uint64_t *, uint64_t *, uint32_t *, cudaStream_t, uint64_t *);
 cudaError_t launch_decode(const uint8_t *, const uint64_t *, uint64_t, uint64_t, uint8_t *, uint32_t *, cudaStream_t,
                           uint64_t *);
+cudaError_t launch_decode_seg(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, uint64_t, uint64_t, uint8_t *,
+                              uint32_t *, cudaStream_t, uint64_t *);
+const uint4 *index_starts(void *, uint64_t);
 size_t index_workspace_bytes(uint64_t);
 cudaError_t run_index(const uint8_t *, uint64_t, uint64_t, uint64_t, uint64_t *, uint32_t *, void *, cudaStream_t,
                       uint64_t *);
@@ -189,6 +192,36 @@ int snappy_b200_index_device(const uint8_t *d_stream, uint64_t stream_bytes, uin
     return SNAPPY_B200_OK;
 }
 
+int snappy_b200_decode_segments_device(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
+                                       uint64_t total_out, uint8_t *d_out, const uint64_t *d_block_offsets,
+                                       uint32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (!d_stream || !d_block_offsets || !d_status || !d_workspace || (!d_out && total_out))
+        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    if (workspace_bytes < index_workspace_bytes(stream_bytes))
+        return fail(SNAPPY_B200_ERR_ARG, "workspace too small");
+    uint64_t launches = 0;
+    cudaError_t e = launch_decode_seg(d_stream, body_offset, d_block_offsets, index_starts(d_workspace, stream_bytes),
+                                      (total_out + kBlock - 1) / kBlock, total_out, d_out, d_status,
+                                      static_cast<cudaStream_t>(stream), &launches);
+    g_launches += launches;
+    if (e != cudaSuccess)
+        return cuda_fail(e, "decode launch");
+    return SNAPPY_B200_OK;
+}
+
+int snappy_b200_decompress_device(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
+                                  uint64_t total_out, uint8_t *d_out, uint64_t *d_block_offsets, uint32_t *d_status,
+                                  void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    int rc = snappy_b200_index_device(d_stream, stream_bytes, body_offset, total_out, d_block_offsets, d_status,
+                                      d_workspace, workspace_bytes, stream);
+    if (rc != SNAPPY_B200_OK)
+        return rc;
+    return snappy_b200_decode_segments_device(d_stream, stream_bytes, body_offset, total_out, d_out, d_block_offsets,
+                                              d_status, d_workspace, workspace_bytes, stream);
+}
+
 } // extern "C"
 
 // ----------------------------------------------------------------------------- host-buffer API
@@ -357,11 +390,8 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
     if ((e = cudaMemcpyAsync(d_stream, stream, stream_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
         (e = cudaMemsetAsync(d_small, 0, 16, st)) != cudaSuccess)
         return cuda_fail(e, "H2D copy");
-    int rc = snappy_b200_index_device(d_stream, stream_bytes, hdr, total, d_offsets, d_status, g_ctx.buf[2],
-                                      g_ctx.cap[2], st);
-    if (rc != SNAPPY_B200_OK)
-        return rc;
-    rc = snappy_b200_decompress_device_indexed(d_stream, d_offsets, nb, total, d_out, d_status, st);
+    int rc = snappy_b200_decompress_device(d_stream, stream_bytes, hdr, total, d_out, d_offsets, d_status, g_ctx.buf[2],
+                                           g_ctx.cap[2], st);
     if (rc != SNAPPY_B200_OK)
         return rc;
     if ((e = cudaMemcpyAsync(g_ctx.h_small, d_small, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||

@@ -1,33 +1,37 @@
-// decode.cu -- K4/K5: one warp per 64 KiB output block, 32 stream bytes per step.
+// decode.cu -- K4/K5: decompression, one warp per 64 KiB output block.
 //
 // reference: decompressor src/snappy_decompression.c:290-333 (tag dispatch), do_literal
 // :193-224, write_literal :232-239, do_copy :253-265, write_copy :273-280.
 //
-// The reference walks one element at a time.  Here a warp looks at a 32-byte window of the
-// compressed block per step:
-//   1. every lane decodes the byte at its offset as if an element started there (tag, header
-//      length, output length, literal source / copy offset);
-//   2. the lanes that really are element starts are the orbit of lane 0 under
-//      "next = lane + element size"; it is found with pointer doubling over shuffles and five
-//      warp-wide OR reductions instead of a serial walk;
-//   3. a warp prefix sum of the output lengths of those lanes gives every element its output
-//      offset;
-//   4. the output bytes of the whole window are then produced 32 at a time, one byte per lane:
-//      a lane finds its element from a bit map of the element starts inside the round, then
-//      reads either the stream (literal) or the output written earlier (copy; offset < length
-//      repeats the pattern, write_copy :273-280).  A source byte that is produced by the very
-//      same round is followed back through the round's elements until it leaves the round or
-//      lands in a literal.
+// The reference walks one element at a time.  Both kernels here decode up to 32 elements per
+// step, one per lane, and then produce the output bytes of all of them 32 at a time:
+//   * a warp prefix sum of the output lengths gives every element its output offset;
+//   * the elements go into a small shared-memory table; in every round the lane that produces
+//     output byte k finds its element from a bit map of the element starts inside the round
+//     (rank = #elements before the round + popc(map up to k) - 1), then reads either the
+//     stream (literal) or the output written earlier (copy; offset < length repeats the
+//     pattern, write_copy :273-280).  A source byte produced by the very same round is
+//     followed back through the round's elements until it leaves the round or lands in a
+//     literal.
 // Literals of 64 bytes or more are moved by the 16-byte copy loop, and the rare element kinds
 // whose header does not fit the 4 bytes a lane holds (copy-4, 4-byte literal length) take a
-// one-element path.  Copies read the output through global memory; one __syncwarp() per step
-// orders the read-after-write.  Unlike the reference, malformed input is detected and
-// reported in *status instead of being undefined behaviour.
+// one-element path.  Copies read the output through global memory; __syncwarp() orders the
+// read-after-write.  Unlike the reference, malformed input is detected and reported in
+// *status instead of being undefined behaviour.
+//
+// What differs is how a step finds its elements:
+//   k_decode_seg   (index-less streams, after K0) takes them from the exact element-start bit
+//                  maps K0 leaves per 128-byte stream segment: lane r gets the r-th start.
+//   k_decode_warp  (caller supplied block index, no K0) looks at a 32-byte window: every lane
+//                  decodes the byte at its offset as if an element started there, and the
+//                  real starts are the orbit of lane 0 under "next = lane + element size",
+//                  found with pointer doubling over shuffles and five warp-wide OR reductions.
 #include "common.cuh"
 
 namespace sb200 {
 
 constexpr uint32_t kLongLiteral = 64;
+constexpr uint32_t kSegBytes = 128; // K0 segment size (csrc/index.cu)
 
 // Little-endian 32 bits at an arbitrarily aligned address; the aligned words touched are
 // clamped to `last_word`, the last aligned word that still holds a byte of the stream.
@@ -41,14 +45,285 @@ __device__ __forceinline__ uint32_t ld_le32_any(const uint8_t *__restrict__ p, c
     return __funnelshift_r(__ldg(w0), __ldg(w1), (uint32_t)(a & 3u) * 8u);
 }
 
+struct Header {
+    uint32_t hdr;  // header bytes (tag + extra)
+    uint32_t len;  // output bytes
+    uint32_t info; // literal: stream position of its bytes; copy: offset
+    bool is_lit;
+    bool slow; // header does not fit in the 4 bytes of v
+};
+
+// Decodes the element whose first 4 stream bytes are v and whose tag sits at stream position pos.
+__device__ __forceinline__ Header decode_header(uint32_t v, uint32_t pos)
+{
+    Header h;
+    const uint32_t tag = v & 0xffu;
+    const uint32_t type = tag & 3u;
+    h.slow = false;
+    h.is_lit = type == 0;
+    if (type == 0) {
+        const uint32_t m = tag >> 2;
+        if (m < 60) {
+            h.hdr = 1;
+            h.len = m + 1;
+        } else {
+            const uint32_t k = m - 59; // 1..4 length bytes
+            h.hdr = 1 + k;
+            h.slow = k == 4;
+            h.len = ((v >> 8) & (0xffffffu >> (8 * (3 - min(k, 3u))))) + 1;
+        }
+        h.info = pos + h.hdr;
+    } else if (type == 1) {
+        h.hdr = 2;
+        h.len = ((tag >> 2) & 7u) + 4;
+        h.info = ((tag >> 5) << 8) | ((v >> 8) & 0xffu);
+    } else if (type == 2) {
+        h.hdr = 3;
+        h.len = (tag >> 2) + 1;
+        h.info = (v >> 8) & 0xffffu;
+    } else {
+        h.hdr = 5;
+        h.len = (tag >> 2) + 1;
+        h.info = 0;
+        h.slow = true;
+    }
+    return h;
+}
+
+// One element, handled by the whole warp (warp-uniform arguments): long literals, copy-4,
+// literals with a 4-byte length.  `in` + ip is the tag, lim the end of the compressed block.
+// Returns an error status or 0; advances ip / op.
+__device__ __forceinline__ uint32_t single_element(const uint8_t *__restrict__ in, uint32_t lim, uint32_t t0,
+                                                   uint8_t *out, uint32_t olen, uint64_t blk, uint32_t &ip, uint32_t &op,
+                                                   uint32_t lane)
+{
+    const uint32_t tg = t0 & 0xffu;
+    const uint32_t ty = tg & 3u;
+    const uint32_t b4 = (ip + 4 < lim) ? (uint32_t)__ldg(in + ip + 4) : 0u;
+    uint32_t h, l;
+    if (ty == 0) {
+        const uint32_t m = tg >> 2;
+        const uint32_t k = m >= 60 ? m - 59 : 0;
+        h = 1 + k;
+        const uint32_t raw = (t0 >> 8) | (b4 << 24);
+        l = k == 0 ? m : (k == 4 ? raw : raw & ((1u << (8 * k)) - 1u));
+        if (ip + h > lim || l >= olen - op || (uint64_t)ip + h + l + 1 > lim)
+            return (ip + h <= lim && (uint64_t)ip + h + l + 1 <= lim) ? SNAPPY_B200_ST_FRAMING
+                                                                      : SNAPPY_B200_ST_CORRUPT;
+        l += 1;
+        coop_copy_ro(out + op, in + ip + h, l, lane, 32);
+        ip += h + l;
+    } else {
+        uint32_t off;
+        if (ty == 1) {
+            h = 2, l = ((tg >> 2) & 7u) + 4, off = ((tg >> 5) << 8) | ((t0 >> 8) & 0xffu);
+        } else if (ty == 2) {
+            h = 3, l = (tg >> 2) + 1, off = (t0 >> 8) & 0xffffu;
+        } else { // copy-4 (src/snappy_decompression.c:323-327)
+            h = 5, l = (tg >> 2) + 1, off = (t0 >> 8) | (b4 << 24);
+        }
+        if (ip + h > lim || off == 0)
+            return SNAPPY_B200_ST_CORRUPT;
+        if (off > op || l > olen - op)
+            return ((uint64_t)off > blk * (uint64_t)kBlock + op) ? SNAPPY_B200_ST_CORRUPT : SNAPPY_B200_ST_FRAMING;
+        __syncwarp();
+        for (uint32_t i = lane; i < l; i += 32)
+            out[op + i] = out[op - off + (off >= l ? i : i % off)];
+        ip += h;
+    }
+    op += l;
+    __syncwarp();
+    return 0;
+}
+
+// Produces T output bytes at out[op ..) from the ne elements in `elems`
+// ({window-relative start, len, literal flag | info, 2^16/offset+1 or 0}).
+__device__ __forceinline__ void produce(const uint8_t *__restrict__ in, uint8_t *out, uint32_t op, uint32_t T,
+                                        const uint4 *elems, uint32_t ne, uint32_t lane)
+{
+    const uint32_t my_start = lane < ne ? elems[lane].x : 0xffffffffu;
+    for (uint32_t c = 0; c < T; c += 32) {
+        const uint32_t before = __popc(__ballot_sync(kFull, my_start < c));
+        const uint32_t rel = my_start - c;
+        const unsigned B = __reduce_or_sync(kFull, rel < 32u ? 1u << rel : 0u);
+        uint32_t k = c + lane; // window-relative output byte
+        bool pending = k < T;
+        uint32_t val = 0;
+        do {
+            if (pending) {
+                const uint32_t r = before + __popc(B & (0xffffffffu >> (31u - (k - c)))) - 1u;
+                const uint4 e = elems[r];
+                const uint32_t i = k - e.x;
+                if (e.z & 0x80000000u) {
+                    val = __ldg(in + (e.z & 0x7fffffffu) + i); // write_literal :232-239
+                    pending = false;
+                } else {
+                    const uint32_t off = e.z;
+                    // write_copy :273-280: byte i comes from i mod offset when the copy overlaps itself
+                    const uint32_t s = e.w ? i - off * ((i * e.w) >> 16) : i;
+                    const uint32_t src = op + e.x + s - off; // block-relative, >= 0 (checked by the caller)
+                    if (src < op + c) {
+                        val = out[src]; // written by an earlier step or an earlier round
+                        pending = false;
+                    } else {
+                        k = src - op; // produced by this very round: follow it back
+                    }
+                }
+            }
+        } while (__any_sync(kFull, pending));
+        if (c + lane < T)
+            out[op + c + lane] = (uint8_t)val;
+        __syncwarp(); // the next round may read what this one wrote
+    }
+}
+
+// Shared tail of a step: prefix sum, validation, table, production.  `mine` lanes hold an
+// element (h, at stream position pos relative to `in`, lim = end of the compressed block);
+// rank = number of element lanes below, ne = their total.  Returns an error status or 0; adds
+// the produced bytes to op.
+__device__ __forceinline__ uint32_t run_step(const uint8_t *__restrict__ in, uint32_t lim, uint8_t *out, uint32_t olen,
+                                             uint32_t &op, bool mine, uint32_t rank, uint32_t ne, const Header &h,
+                                             uint32_t pos, uint4 *elems, uint32_t lane)
+{
+    const uint32_t mylen = mine ? h.len : 0u;
+    uint32_t end = mylen;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, end, d);
+        if ((int)lane >= d)
+            end += t;
+    }
+    const uint32_t T = __shfl_sync(kFull, end, 31);
+    const uint32_t start = end - mylen; // window-relative output offset of my element
+    const bool bad_corrupt = mine && (pos + h.hdr > lim || (h.is_lit && pos + h.hdr + h.len > lim) ||
+                                      (!h.is_lit && h.info == 0));
+    bool bad_framing = mine && !h.is_lit && h.info > op + start;
+    if (T > olen - op)
+        bad_framing = true;
+    const unsigned BC = __ballot_sync(kFull, bad_corrupt), BF = __ballot_sync(kFull, bad_framing);
+    if (BC | BF)
+        return BC ? SNAPPY_B200_ST_CORRUPT : SNAPPY_B200_ST_FRAMING;
+    if (mine) {
+        // small offsets repeat their pattern (offset < length): keep 2^16/offset for "i mod offset"
+        const uint32_t inv = (!h.is_lit && h.info < h.len) ? 65536u / h.info + 1u : 0u;
+        elems[rank] = make_uint4(start, h.len, h.info | (h.is_lit ? 0x80000000u : 0u), inv);
+    }
+    __syncwarp(); // also: stores of earlier steps are visible to every lane from here
+    produce(in, out, op, T, elems, ne, lane);
+    op += T;
+    return 0;
+}
+
+// ------------------------------------------------------------------ segment-driven decoder
+// r-th (0-based) set bit of a 128-bit map.
+__device__ __forceinline__ uint32_t nth_set_bit128(const uint32_t R[4], uint32_t r)
+{
+    const uint32_t c0 = __popc(R[0]), c1 = c0 + __popc(R[1]), c2 = c1 + __popc(R[2]);
+    const uint32_t w = (r >= c0) + (r >= c1) + (r >= c2);
+    const uint32_t below = w == 0 ? 0u : (w == 1 ? c0 : (w == 2 ? c1 : c2));
+    const uint32_t W = w == 0 ? R[0] : (w == 1 ? R[1] : (w == 2 ? R[2] : R[3]));
+    const uint32_t rr = r - below;
+    uint32_t p = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1)
+        if ((uint32_t)__popc(W & ((1u << (p + s)) - 1u)) <= rr)
+            p += s;
+    return w * 32 + p;
+}
+
+__global__ void __launch_bounds__(32) k_decode_seg(const uint8_t *__restrict__ stream, uint64_t body_offset,
+                                                   const uint64_t *__restrict__ offsets,
+                                                   const uint4 *__restrict__ starts, uint64_t total_out,
+                                                   uint8_t *out_base, uint32_t *__restrict__ status)
+{
+    __shared__ uint4 elems[32];
+    const uint32_t lane = threadIdx.x;
+    const uint64_t blk = blockIdx.x;
+    if (*reinterpret_cast<volatile uint32_t *>(status) != 0)
+        return; // K0 rejected the stream: its maps are not trustworthy
+    const uint64_t c0 = offsets[blk], c1 = offsets[blk + 1];
+    const uint64_t stream_bytes = offsets[gridDim.x];
+    if (c1 <= c0 || c0 < body_offset || c1 > stream_bytes || c1 - c0 > 2u * kBlock) {
+        if (lane == 0)
+            atomicOr(status, SNAPPY_B200_ST_CORRUPT);
+        return;
+    }
+    const uint32_t *last_word = reinterpret_cast<const uint32_t *>(
+        reinterpret_cast<uintptr_t>(stream + stream_bytes - 1) & ~uintptr_t(3));
+    // stream positions below are relative to the first segment the block touches
+    const uint64_t b0 = c0 - body_offset, b1 = c1 - body_offset; // body-relative
+    const uint64_t t0 = b0 / kSegBytes, t1 = (b1 - 1) / kSegBytes;
+    const uint8_t *__restrict__ in = stream + body_offset + t0 * kSegBytes;
+    const uint32_t first = (uint32_t)(b0 - t0 * kSegBytes); // where the block starts
+    const uint32_t lim = (uint32_t)(b1 - t0 * kSegBytes);   // where it ends
+    uint8_t *out = out_base + blk * (uint64_t)kBlock;
+    const uint64_t oleft = total_out - blk * (uint64_t)kBlock;
+    const uint32_t olen = oleft < kBlock ? (uint32_t)oleft : kBlock;
+
+    uint32_t op = 0, err = 0;
+    for (uint64_t t = t0; t <= t1 && !err; ++t) {
+        const uint4 sv = __ldg(starts + t);
+        uint32_t R[4] = {sv.x, sv.y, sv.z, sv.w};
+        const uint32_t seg_lo = (uint32_t)((t - t0) * kSegBytes);
+        // keep only the starts that belong to this block
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t lo = seg_lo + 32 * w; // stream position of bit 0 of this word
+            if (lo + 32 <= first || lo >= lim) {
+                R[w] = 0;
+            } else {
+                if (lo < first)
+                    R[w] &= ~((1u << (first - lo)) - 1u);
+                if (lo + 32 > lim)
+                    R[w] &= (1u << (lim - lo)) - 1u;
+            }
+        }
+        while ((R[0] | R[1] | R[2] | R[3]) && !err) {
+            const uint32_t cnt = __popc(R[0]) + __popc(R[1]) + __popc(R[2]) + __popc(R[3]);
+            uint32_t ne = min(cnt, 32u);
+            const uint32_t bit = nth_set_bit128(R, min(lane, ne - 1));
+            const uint32_t pos = seg_lo + bit;
+            const uint32_t v = ld_le32_any(in + pos, last_word);
+            const Header h = decode_header(v, pos);
+            const bool special = h.slow || (h.is_lit && h.len >= kLongLiteral);
+            const unsigned S = __ballot_sync(kFull, lane < ne && special);
+            if (S & 1u) {
+                uint32_t ip = __shfl_sync(kFull, pos, 0);
+                const uint32_t v0 = __shfl_sync(kFull, v, 0);
+                err = single_element(in, lim, v0, out, olen, blk, ip, op, lane);
+                ne = 1;
+            } else {
+                if (S)
+                    ne = __ffs((int)S) - 1;
+                err = run_step(in, lim, out, olen, op, lane < ne, lane, ne, h, pos, elems, lane);
+            }
+            // drop the ne starts just consumed
+            const uint32_t lastbit = __shfl_sync(kFull, bit, ne - 1);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                if (lastbit >= 32u * w + 31u)
+                    R[w] = 0;
+                else if (lastbit >= 32u * w)
+                    R[w] &= ~((2u << (lastbit - 32u * w)) - 1u);
+            }
+        }
+    }
+    if (!err && op != olen)
+        err = SNAPPY_B200_ST_CORRUPT;
+    if (err && lane == 0)
+        atomicOr(status, err);
+}
+
+// ------------------------------------------------------------------ window decoder (block index only)
 __global__ void __launch_bounds__(32) k_decode_warp(const uint8_t *__restrict__ stream,
                                                     const uint64_t *__restrict__ offsets, uint64_t total_out,
                                                     uint8_t *out_base, uint32_t *__restrict__ status)
 {
+    __shared__ uint4 elems[32];
     const uint32_t lane = threadIdx.x;
     const uint64_t blk = blockIdx.x;
     if (*reinterpret_cast<volatile uint32_t *>(status) != 0)
-        return; // an earlier stage (K0) rejected the stream: the offsets are not trustworthy
+        return; // an earlier stage rejected the stream: the offsets are not trustworthy
     const uint64_t c0 = offsets[blk], c1 = offsets[blk + 1];
     const uint64_t stream_bytes = offsets[gridDim.x]; // entry n_blocks of the index = end of the stream
     const uint64_t clen64 = c1 - c0;
@@ -65,53 +340,21 @@ __global__ void __launch_bounds__(32) k_decode_warp(const uint8_t *__restrict__ 
     const uint32_t olen = oleft < kBlock ? (uint32_t)oleft : kBlock;
     const uint32_t clen = (uint32_t)clen64;
 
-    __shared__ uint4 elems[32]; // the elements of the current window: {start, len, literal|info, 2^16/offset}
-
     uint32_t ip = 0, op = 0;
     uint32_t err = 0;
-    while (op < olen) {
+    while (op < olen && !err) {
         if (ip >= clen) {
             err = SNAPPY_B200_ST_CORRUPT;
             break;
         }
-        // ---- 1. speculative decode of the element that would start at ip + lane
+        // ---- speculative decode of the element that would start at ip + lane
         const uint32_t pos = ip + lane;
         const bool inside = pos < clen;
         const uint32_t v = ld_le32_any(in + (inside ? pos : clen - 1), last_word);
-        const uint32_t tag = v & 0xffu;
-        const uint32_t type = tag & 3u;
-        uint32_t hdr, len, info; // info: literal -> stream position of its bytes, copy -> offset
-        bool slow = false;       // header does not fit in v (needs the one-element path)
-        if (type == 0) {
-            const uint32_t m = tag >> 2;
-            if (m < 60) {
-                hdr = 1;
-                len = m + 1;
-            } else {
-                const uint32_t k = m - 59; // 1..4 length bytes
-                hdr = 1 + k;
-                slow = k == 4;
-                len = ((v >> 8) & (0xffffffu >> (8 * (3 - min(k, 3u))))) + 1;
-            }
-            info = pos + hdr;
-        } else if (type == 1) {
-            hdr = 2;
-            len = ((tag >> 2) & 7u) + 4;
-            info = ((tag >> 5) << 8) | ((v >> 8) & 0xffu);
-        } else if (type == 2) {
-            hdr = 3;
-            len = (tag >> 2) + 1;
-            info = (v >> 8) & 0xffffu;
-        } else {
-            hdr = 5;
-            len = (tag >> 2) + 1;
-            info = 0;
-            slow = true;
-        }
-        const bool is_lit = type == 0;
-        const uint32_t size = hdr + (is_lit ? len : 0u); // stream bytes of the element
+        const Header h = decode_header(v, pos);
+        const uint32_t size = h.hdr + (h.is_lit ? h.len : 0u); // stream bytes of the element
 
-        // ---- 2. which lanes are element starts: orbit of lane 0 under lane -> lane + size
+        // ---- which lanes are element starts: orbit of lane 0 under lane -> lane + size
         // (an element that ends at or past the end of the compressed block leaves the window)
         uint32_t j0 = (inside && pos + size < clen) ? min(lane + size, 32u) : 32u;
         uint32_t j1 = __shfl_sync(kFull, j0, j0 & 31);
@@ -130,130 +373,24 @@ __global__ void __launch_bounds__(32) k_decode_warp(const uint8_t *__restrict__ 
         M |= __reduce_or_sync(kFull, ((M >> lane) & 1u) && j0 < 32 ? 1u << j0 : 0u);
 
         // cut the step before the first element that needs special handling
-        const bool special = slow || (is_lit && len >= kLongLiteral);
+        const bool special = h.slow || (h.is_lit && h.len >= kLongLiteral);
         const unsigned S = __ballot_sync(kFull, ((M >> lane) & 1u) && special);
         if (S & 1u) {
-            // ---- one-element path for the element at ip (uniform: every lane recomputes it)
-            const uint32_t t0 = __shfl_sync(kFull, v, 0);
-            const uint32_t tg = t0 & 0xffu;
-            const uint32_t ty = tg & 3u;
-            const uint32_t b4 = (ip + 4 < clen) ? (uint32_t)__ldg(in + ip + 4) : 0u;
-            uint32_t h, l, off = 0;
-            if (ty == 0) {
-                const uint32_t m = tg >> 2;
-                const uint32_t k = m >= 60 ? m - 59 : 0;
-                h = 1 + k;
-                const uint32_t raw = (t0 >> 8) | (b4 << 24);
-                l = k == 0 ? m : (k == 4 ? raw : raw & ((1u << (8 * k)) - 1u));
-                if (ip + h > clen || l >= olen - op || (uint64_t)ip + h + l + 1 > clen) {
-                    err = (ip + h <= clen && (uint64_t)ip + h + l + 1 <= clen) ? SNAPPY_B200_ST_FRAMING
-                                                                             : SNAPPY_B200_ST_CORRUPT;
-                    break;
-                }
-                l += 1;
-                coop_copy_ro(out + op, in + ip + h, l, lane, 32);
-                ip += h + l;
-            } else {
-                // copy-4 (src/snappy_decompression.c:323-327)
-                h = 5;
-                l = (tg >> 2) + 1;
-                off = (t0 >> 8) | (b4 << 24);
-                if (ip + h > clen || off == 0) {
-                    err = SNAPPY_B200_ST_CORRUPT;
-                    break;
-                }
-                if (off > op || l > olen - op) {
-                    err = ((uint64_t)off > blk * (uint64_t)kBlock + op) ? SNAPPY_B200_ST_CORRUPT
-                                                                        : SNAPPY_B200_ST_FRAMING;
-                    break;
-                }
-                __syncwarp();
-                for (uint32_t i = lane; i < l; i += 32)
-                    out[op + i] = out[op - off + (off >= l ? i : i % off)];
-                ip += h;
-            }
-            op += l;
-            __syncwarp();
+            const uint32_t v0 = __shfl_sync(kFull, v, 0);
+            err = single_element(in, clen, v0, out, olen, blk, ip, op, lane);
             continue;
         }
         if (S)
             M &= (1u << (__ffs((int)S) - 1)) - 1u;
         const bool mine = (M >> lane) & 1u;
-
-        // ---- 3. output offsets (inclusive prefix sum; non-element lanes contribute nothing)
-        const uint32_t mylen = mine ? len : 0u;
-        uint32_t end = mylen;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFull, end, d);
-            if ((int)lane >= d)
-                end += t;
-        }
-        const uint32_t T = __shfl_sync(kFull, end, 31);
-        const uint32_t start = end - mylen; // window-relative output offset of my element
-        // validation
-        bool bad_corrupt = mine && (!inside || pos + hdr > clen || (is_lit && pos + size > clen) ||
-                                    (!is_lit && info == 0));
-        bool bad_framing = mine && !is_lit && info > op + start;
-        if (T > olen - op)
-            bad_framing = true;
-        const unsigned BC = __ballot_sync(kFull, bad_corrupt), BF = __ballot_sync(kFull, bad_framing);
-        if (BC | BF) {
-            err = BC ? SNAPPY_B200_ST_CORRUPT : SNAPPY_B200_ST_FRAMING;
-            break;
-        }
         const int last = 31 - __clz((int)M);
         const uint32_t consumed = __shfl_sync(kFull, lane + size, last);
-
-        // ---- 4. produce T output bytes, 32 per round
-        // The elements of the window are compacted into a small shared-memory table (rank =
-        // number of element lanes below mine).  In every round the lane that produces output
-        // byte k finds its element from a 32-bit map of the element starts inside the round:
-        // rank = (#elements starting before the round) + popc(map up to k) - 1.
-        const uint32_t rank = __popc(M & ((1u << lane) - 1u));
-        if (mine) {
-            // small offsets repeat their pattern (offset < length): keep 2^16/offset for "i mod offset"
-            const uint32_t inv = (!is_lit && info < len) ? 65536u / info + 1u : 0u;
-            elems[rank] = make_uint4(start, len, info | (is_lit ? 0x80000000u : 0u), inv);
+        if (__ballot_sync(kFull, mine && !inside)) {
+            err = SNAPPY_B200_ST_CORRUPT;
+            break;
         }
-        __syncwarp(); // also: stores of earlier steps are visible to every lane from here
-        const uint32_t ne = __popc(M);
-        const uint32_t my_start = lane < ne ? elems[lane].x : 0xffffffffu;
-        for (uint32_t c = 0; c < T; c += 32) {
-            const uint32_t before = __popc(__ballot_sync(kFull, my_start < c));
-            const uint32_t rel = my_start - c;
-            const unsigned B = __reduce_or_sync(kFull, rel < 32u ? 1u << rel : 0u);
-            uint32_t k = c + lane; // window-relative output byte
-            bool pending = k < T;
-            uint32_t val = 0;
-            do {
-                if (pending) {
-                    const uint32_t r = before + __popc(B & (0xffffffffu >> (31u - (k - c)))) - 1u;
-                    const uint4 e = elems[r];
-                    const uint32_t i = k - e.x;
-                    if (e.z & 0x80000000u) {
-                        val = __ldg(in + (e.z & 0x7fffffffu) + i); // write_literal :232-239
-                        pending = false;
-                    } else {
-                        const uint32_t off = e.z;
-                        // write_copy :273-280: byte i comes from i mod offset when the copy overlaps itself
-                        const uint32_t s = e.w ? i - off * ((i * e.w) >> 16) : i;
-                        const uint32_t src = op + e.x + s - off; // block-relative, >= 0 (checked above)
-                        if (src < op + c) {
-                            val = out[src]; // written by an earlier step or an earlier round
-                            pending = false;
-                        } else {
-                            k = src - op; // produced by this very round: follow it back
-                        }
-                    }
-                }
-            } while (__any_sync(kFull, pending));
-            if (c + lane < T)
-                out[op + c + lane] = (uint8_t)val;
-            __syncwarp(); // the next round may read what this one wrote
-        }
+        err = run_step(in, clen, out, olen, op, mine, __popc(M & ((1u << lane) - 1u)), __popc(M), h, pos, elems, lane);
         ip += consumed;
-        op += T;
     }
     if (!err && ip != clen)
         err = SNAPPY_B200_ST_CORRUPT; // the index said this block ends at c1
@@ -269,6 +406,20 @@ cudaError_t launch_decode(const uint8_t *d_stream, const uint64_t *d_offsets, ui
     if (n_blocks > 0x7fffffffull)
         return cudaErrorInvalidValue;
     k_decode_warp<<<(unsigned)n_blocks, 32, 0, st>>>(d_stream, d_offsets, total_out, d_out, d_status);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_seg(const uint8_t *d_stream, uint64_t body_offset, const uint64_t *d_offsets,
+                              const uint4 *d_starts, uint64_t n_blocks, uint64_t total_out, uint8_t *d_out,
+                              uint32_t *d_status, cudaStream_t st, uint64_t *launches)
+{
+    if (n_blocks == 0)
+        return cudaSuccess;
+    if (n_blocks > 0x7fffffffull)
+        return cudaErrorInvalidValue;
+    k_decode_seg<<<(unsigned)n_blocks, 32, 0, st>>>(d_stream, body_offset, d_offsets, d_starts, total_out, d_out,
+                                                    d_status);
     *launches += 1;
     return cudaGetLastError();
 }

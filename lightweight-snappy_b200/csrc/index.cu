@@ -32,7 +32,8 @@
 //                      corrected instead of one per round.  An adversarial stream degrades to
 //                      sequential but stays correct.  k_group_final then chases every live group
 //                      once more from its true entry and records the entry of each segment.
-//   C  k_index_outlen  every live segment sums the output bytes of its elements
+//   C  k_index_outlen  every live segment sums the output bytes of its elements and stores the
+//                      exact bit map of its element starts (for the segment-driven decoder)
 //      k_scan_*        exclusive scan -> output offset of every segment
 //   D  k_index_blocks  every live segment walks once more and records the stream offset of
 //                      each element that starts a 64 KiB output block; elements that straddle
@@ -421,15 +422,19 @@ __global__ void __launch_bounds__(kGroupCta) k_group_final(const uint8_t *__rest
         entry[s0 + lane + 32] = sm.entry[lane + 32];
 }
 
-// C: output bytes produced by the elements that start in each live segment.
+// C: output bytes produced by the elements that start in each live segment.  The walk visits
+// exactly the true element starts of the segment, so it also replaces the (speculative) path
+// map by the exact map of element starts -- what the segment-driven decoder consumes.
 __global__ void __launch_bounds__(256) k_index_outlen(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
                                                       const uint8_t *__restrict__ entry, uint64_t *__restrict__ outlen,
-                                                      uint32_t *__restrict__ status)
+                                                      uint4 *__restrict__ starts, uint32_t *__restrict__ status)
 {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t >= nseg)
         return;
     uint64_t sum = 0;
+    Path p;
+    p.clear();
     const uint32_t en = entry[t];
     if (!(en & kDead)) {
         const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
@@ -442,11 +447,13 @@ __global__ void __launch_bounds__(256) k_index_outlen(const uint8_t *__restrict_
             }
             if (el.out > kBlock)
                 atomicOr(status, SNAPPY_B200_ST_FRAMING);
+            p.set((uint32_t)(e - lo));
             sum += el.out;
             e += el.size;
         }
     }
     outlen[t] = sum;
+    starts[t] = make_uint4(p.bits[0], p.bits[1], p.bits[2], p.bits[3]);
 }
 
 // Exclusive scan of a u64 array (one entry per 128 stream bytes, so millions of entries): tile
@@ -651,6 +658,9 @@ static IndexWorkspace carve(void *ws, uint64_t stream_bytes)
     return w;
 }
 
+// The exact element-start maps k_index_outlen leaves behind (one uint4 per 128-byte segment).
+const uint4 *index_starts(void *d_ws, uint64_t stream_bytes) { return carve(d_ws, stream_bytes).paths; }
+
 static uint64_t g_last_rounds = 0;
 uint64_t index_last_rounds() { return g_last_rounds; }
 
@@ -710,7 +720,7 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
     }
     k_group_final<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.entry);
     *launches += 1;
-    k_index_outlen<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outlen, d_status);
+    k_index_outlen<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outlen, w.paths, d_status);
     const uint64_t ntile = (nseg + kScanTile - 1) / kScanTile;
     k_scan_tile_sums<<<(unsigned)ntile, kScanCta, 0, st>>>(w.outlen, nseg, w.tile_sums);
     k_scan_tiles<<<1, kScanCta, 0, st>>>(w.tile_sums, ntile, w.total);

@@ -102,6 +102,13 @@ def test_device_api_64mib_against_oracle(oracle, kind):
         assert api.index_rounds() <= 64, f"K0 needed {api.index_rounds()} relaxation rounds"
         want_offs, _ = oracle.block_index(want)
         assert np.array_equal(offs.astype(np.uint64), want_offs)
+        # ... and the whole index-less path: K0 + segment-driven decoder
+        out2 = torch.zeros(host_m.size, dtype=torch.uint8, device="cuda")
+        offs3 = torch.zeros(nb + 1, dtype=torch.int64, device="cuda")
+        codec.decompress(codec.stream_buf, got.size, hdr, host_m.size, out2, offs3)
+        codec.check_status()
+        assert torch.equal(out2, data_m), "index-less decode"
+        assert np.array_equal(offs3.cpu().numpy(), offs)
 
 
 def test_decoder_foreign_and_malformed_streams(oracle):

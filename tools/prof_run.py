@@ -21,7 +21,7 @@ for _ in range(a.reps):
     while (n >> (7 * hdr)) > 0:
         hdr += 1
     idx = torch.zeros_like(codec.block_offsets)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record()
     codec.index(codec.stream_buf, s.numel(), hdr, n, idx)
     ev[1].record()
@@ -29,5 +29,12 @@ for _ in range(a.reps):
     ev[2].record()
     codec.check_status()
     assert torch.equal(out, data)
+    out.zero_()
+    ev[3].record()
+    codec.decompress(codec.stream_buf, s.numel(), hdr, n, out, idx)
+    ev[4].record()
+    codec.check_status()
+    assert torch.equal(out, data)
     print(f"{a.kind} {a.mib} MiB mode {a.mode}: ratio {n / s.numel():.3f}, K0 rounds {api.index_rounds()}, "
-          f"index {ev[0].elapsed_time(ev[1]):.3f} ms, decode {ev[1].elapsed_time(ev[2]):.3f} ms")
+          f"index {ev[0].elapsed_time(ev[1]):.3f} ms, window decode {ev[1].elapsed_time(ev[2]):.3f} ms, "
+          f"index+segment decode {ev[3].elapsed_time(ev[4]):.3f} ms")
