@@ -18,13 +18,15 @@
 // not write compressed bytes: it leaves one 8-byte record per copy {position, offset,
 // length, literal run before it}.
 //
-// Hash-mode table entry: (16-bit key fingerprint << 16) | u16 position.  The fingerprint is
-// bits 19..4 of key*0x1e35a7bd -- together with the 12-bit slot index it pins 28 of the 32
-// bits of an injective function of the key, so the "does the candidate's 4 bytes equal mine"
-// test of the reference (found_match, :259-265) is almost always answered from shared memory;
-// lanes whose fingerprint matches confirm against the candidate bytes, all at once.  The
-// reference's zero-filled table ("candidate = position 0") becomes (fingerprint of the
-// block's first 4 bytes, 0).
+// Hash-mode table: u16 position + u8 key fingerprint per slot, in two arrays (8 + 4 KiB, so 18
+// blocks fit in one SM's shared memory).  The fingerprint is bits 19..12 of key*0x1e35a7bd --
+// together with the 12-bit slot index it pins 20 of the 32 bits of an injective function of
+// the key, so the "does the candidate's 4 bytes equal mine" test of the reference
+// (found_match, :259-265) is almost always answered from shared memory; lanes whose
+// fingerprint matches confirm against the candidate bytes, all at once, and compare the next
+// four bytes in the same fetch (most matches end there, which saves the separate extension
+// round trip).  The reference's zero-filled table ("candidate = position 0") becomes
+// (position 0, fingerprint of the block's first 4 bytes).
 //
 // Exact mode keeps an open-addressing table of u16 positions keyed by the exact 4 bytes
 // (0xffff = empty, which no insertable position can be: positions >= n-15 are never probed).
@@ -143,7 +145,8 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
     constexpr uint32_t C = MODE == 0 ? 1 : 2;
     constexpr uint32_t D = MODE == 0 ? 0 : 1;
 
-    uint32_t *htab = reinterpret_cast<uint32_t *>(smem_raw);
+    uint16_t *hpos = reinterpret_cast<uint16_t *>(smem_raw);   // hash mode: candidate position per slot
+    uint8_t *hfp = smem_raw + 2 * SNAPPY_B200_HTABLE_SIZE;     // hash mode: key fingerprint per slot
     ExactTable<LOG_SLOTS> et{reinterpret_cast<uint16_t *>(smem_raw)};
     uint32_t shift = 20;
     uint32_t n_keys = 0; // exact mode: dictionary population (warp-uniform)
@@ -154,11 +157,14 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
         while ((1u << lg) < SNAPPY_B200_HTABLE_SIZE && (1u << lg) < n)
             ++lg;
         shift = 32 - lg;
-        const uint32_t e0 = n >= 4 ? ((ld_be32(b, 0, last_word) * kHashMul) << 12) & 0xffff0000u : 0;
-        const uint4 init = make_uint4(e0, e0, e0, e0);
-        uint4 *t4 = reinterpret_cast<uint4 *>(htab);
-        for (uint32_t i = lane; i < (1u << lg) / 4; i += 32)
-            t4[i] = init;
+        const uint32_t f0 = n >= 4 ? ((ld_be32(b, 0, last_word) * kHashMul) >> 12) & 0xffu : 0;
+        const uint32_t f4 = f0 * 0x01010101u;
+        uint4 *p4 = reinterpret_cast<uint4 *>(hpos);
+        uint4 *q4 = reinterpret_cast<uint4 *>(hfp);
+        for (uint32_t i = lane; i < (1u << lg) / 8; i += 32)
+            p4[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = lane; i < (1u << lg) / 16; i += 32)
+            q4[i] = make_uint4(f4, f4, f4, f4);
     } else {
         uint4 *t4 = reinterpret_cast<uint4 *>(smem_raw);
         const uint4 init = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
@@ -192,22 +198,37 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
         unsigned grp;
         bool in_table = false;
 
+        uint32_t ext4 = 4; // equal bytes among the four that follow the key (4 = unknown / all)
         if (MODE == 0) {
             const uint32_t prod = key * kHashMul; // hash_bytes :81-84
             idx = prod >> shift;
-            ph = (prod << 12) & 0xffff0000u;
+            ph = (prod >> 12) & 0xffu;
             grp = __match_any_sync(kFull, idx);
             const unsigned vis = grp & vis_mask;
             const int src = 31 - __clz((int)vis); // latest earlier writer of the slot (-1: none)
             const uint32_t skey = __shfl_sync(kFull, key, src);
             const uint32_t spos = __shfl_sync(kFull, ev_pos, src);
-            const uint32_t entry = htab[idx];
+            // my next four bytes are the key of the lane 8 up (steps of one byte, two lanes each)
+            const uint32_t nkey = __shfl_down_sync(kFull, key, 8);
+            const bool nend = __shfl_down_sync(kFull, (int)end_j, 8);
+            const bool nkey_ok = lane < 24 && !nend && skip + D + C * 15 < 64;
+            const uint32_t tpos = hpos[idx];
+            const uint32_t tfp = hfp[idx];
             if (vis) {
                 hit = skey == key;
                 cand = spos;
             } else {
-                cand = entry & 0xffffu;
-                hit = probe && ((entry ^ ph) < 0x10000u) && ld_be32(b, cand, last_word) == key; // found_match :259-265
+                cand = tpos;
+                hit = false;
+                if (probe && tfp == ph) {
+                    // found_match :259-265, and a head start on find_copy_length :61-72
+                    const uint32_t c0 = ld_le32(b, cand, last_word);
+                    const uint32_t c1 = ld_le32(b, cand + 4, last_word);
+                    hit = bswap32(c0) == key;
+                    const uint32_t x = bswap32(c1) ^ nkey;
+                    if (nkey_ok && x)
+                        ext4 = (uint32_t)__clz((int)x) >> 3; // big-endian: leading equal bytes
+                }
             }
         } else {
             grp = __match_any_sync(kFull, key);
@@ -230,8 +251,10 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
         const unsigned g = grp & cm;
         if (MODE == 0) {
             // update_hash_table :303-307: in program order the last writer of a slot wins
-            if (g && 31 - __clz((int)g) == (int)lane)
-                htab[idx] = ph | ev_pos;
+            if (g && 31 - __clz((int)g) == (int)lane) {
+                hpos[idx] = (uint16_t)ev_pos;
+                hfp[idx] = (uint8_t)ph;
+            }
         } else {
             // insert-if-absent, src/BST.c:30-43: the first occurrence of a new key is kept
             const bool ins = g && !in_table && __ffs((int)g) - 1 == (int)lane;
@@ -250,8 +273,10 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
             const uint32_t p = __shfl_sync(kFull, ev_pos, f);
             const uint32_t c = __shfl_sync(kFull, cand, f);
             if (MODE == 0) {
-                if ((int)lane == f)
-                    htab[idx] = ph | ev_pos; // emit_copy :327
+                if ((int)lane == f) { // emit_copy :327
+                    hpos[idx] = (uint16_t)ev_pos;
+                    hfp[idx] = (uint8_t)ph;
+                }
             } else {
                 if ((int)lane == f) { // tree.c:221: the found node now points at this position
                     bool fnd;
@@ -260,7 +285,8 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
                     et.tab[s] = (uint16_t)ev_pos;
                 }
             }
-            const uint32_t len = match_extend(b, p, c, n, last_word, lane);
+            const uint32_t e4 = __shfl_sync(kFull, ext4, f);
+            const uint32_t len = e4 < 4 ? 4 + e4 : match_extend(b, p, c, n, last_word, lane);
             if (lane == (nh & 31u))
                 rec = make_uint2(p | ((p - c) << 16), len | ((p - prev_end) << 16));
             ++nh;
@@ -462,7 +488,7 @@ cudaError_t launch_compress(const uint8_t *d_in, uint64_t n_bytes, int mode, uin
         return cudaErrorInvalidValue;
     const dim3 grid((unsigned)nb), cta(32);
     if (mode == SNAPPY_B200_MODE_HASH) {
-        k_parse<0, 12, true><<<grid, cta, 4096 * 4, st>>>(d_in, n_bytes, d_recs, d_nrec, 0);
+        k_parse<0, 12, true><<<grid, cta, 4096 * 3, st>>>(d_in, n_bytes, d_recs, d_nrec, 0);
         *launches += 1;
     } else {
         // exact mode: 8 Ki slots (16 KiB), then 32 Ki slots (64 KiB), then 64 Ki slots (128 KiB)
