@@ -133,6 +133,11 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
                                 uint64_t *out_bytes);
 /* Releases the cached device/pinned buffers of the host-buffer API. */
 void snappy_b200_release(void);
+/* Page-locked host memory for the buffers handed to the host-buffer API (what the reference's
+ * IO_utils.c / Buffer allocations become on this path: with page-locked buffers the copies
+ * overlap with the kernels).  Returns NULL when no device is usable.                       */
+void *snappy_b200_host_alloc(size_t bytes);
+void snappy_b200_host_free(void *p);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,8 @@ SIGNATURES = {
     "snappy_b200_uncompressed_length": (C.c_int, [_u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "snappy_b200_decompress_host": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "snappy_b200_release": (None, []),
+    "snappy_b200_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "snappy_b200_host_free": (None, [C.c_void_p]),
     # the reference's own symbols (drop-in layer)
     "snappy_compress": (None, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
     "snappy_compress_bst": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),

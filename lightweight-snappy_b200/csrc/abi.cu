@@ -21,7 +21,7 @@ cudaError_t launch_decode_seg(const uint8_t *, uint64_t, const uint64_t *, const
 const uint4 *index_starts(void *, uint64_t);
 size_t index_workspace_bytes(uint64_t);
 cudaError_t run_index(const uint8_t *, uint64_t, uint64_t, uint64_t, uint64_t *, uint32_t *, void *, cudaStream_t,
-                      uint64_t *);
+                      uint64_t *, bool, uint64_t);
 uint32_t host_varint_len(uint64_t);
 uint64_t index_last_rounds();
 
@@ -84,6 +84,29 @@ static int status_to_error(uint32_t st)
     if (st)
         return fail(SNAPPY_B200_ERR_CORRUPT, "device status 0x%x", st);
     return SNAPPY_B200_OK;
+}
+
+int fail_msg(int code, const char *msg) { return fail(code, "%s", msg); }
+int cuda_fail_msg(cudaError_t e, const char *what) { return cuda_fail(e, what); }
+int status_error(uint32_t st) { return status_to_error(st); }
+size_t compress_workspace_bytes_internal(uint64_t n_bytes) { return compress_ws_bytes(n_bytes); }
+void add_launches(uint64_t n) { g_launches += n; }
+
+// One chunk of a longer input: blocks only, or (first chunk) the varint of the WHOLE input
+// followed by blocks.  Same kernels as snappy_b200_compress_device.
+cudaError_t compress_chunk(const uint8_t *d_in, uint64_t chunk_bytes, uint64_t varint_value, int mode, uint8_t *d_out,
+                           uint64_t out_capacity, uint64_t *d_out_bytes, uint32_t *d_status, void *d_workspace,
+                           cudaStream_t st)
+{
+    const uint64_t nb = (chunk_bytes + kBlock - 1) / kBlock;
+    CompressWorkspace w = carve_compress(d_workspace, chunk_bytes);
+    uint64_t launches = 0;
+    cudaError_t e = launch_compress(d_in, chunk_bytes, mode, w.scratch, w.sizes, w.recs, w.nrec, st, &launches);
+    if (e == cudaSuccess)
+        e = launch_compact(w.scratch, w.sizes, nb, varint_value, varint_value ? host_varint_len(varint_value) : 0,
+                           varint_value ? 1 : 0, d_out, out_capacity, w.offsets, d_out_bytes, d_status, st, &launches);
+    g_launches += launches;
+    return e;
 }
 
 } // namespace sb200
@@ -185,7 +208,7 @@ int snappy_b200_index_device(const uint8_t *d_stream, uint64_t stream_bytes, uin
         return fail(SNAPPY_B200_ERR_ARG, "workspace too small");
     uint64_t launches = 0;
     cudaError_t e = run_index(d_stream, stream_bytes, body_offset, total_out, d_block_offsets, d_status, d_workspace,
-                              static_cast<cudaStream_t>(stream), &launches);
+                              static_cast<cudaStream_t>(stream), &launches, false, 0);
     g_launches += launches;
     if (e != cudaSuccess)
         return cuda_fail(e, "index launch");
@@ -224,193 +247,3 @@ int snappy_b200_decompress_device(const uint8_t *d_stream, uint64_t stream_bytes
 
 } // extern "C"
 
-// ----------------------------------------------------------------------------- host-buffer API
-namespace sb200 {
-
-// Cached per-process buffers of the synchronous host-buffer entry points.
-struct HostCtx {
-    std::mutex mu;
-    cudaStream_t st = nullptr;
-    void *buf[4] = {nullptr, nullptr, nullptr, nullptr}; // 0 in, 1 out, 2 workspace, 3 small (offsets etc.)
-    size_t cap[4] = {0, 0, 0, 0};
-    uint64_t *h_small = nullptr; // pinned: [0] out_bytes, [1] status
-
-    cudaError_t need(int i, size_t bytes)
-    {
-        bytes = align_up(bytes + 256, 1 << 20);
-        if (cap[i] >= bytes)
-            return cudaSuccess;
-        if (buf[i])
-            cudaFree(buf[i]);
-        buf[i] = nullptr;
-        cap[i] = 0;
-        cudaError_t e = cudaMalloc(&buf[i], bytes);
-        if (e == cudaSuccess)
-            cap[i] = bytes;
-        return e;
-    }
-    cudaError_t init()
-    {
-        cudaError_t e = cudaSuccess;
-        if (!st)
-            e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-        if (e == cudaSuccess && !h_small)
-            e = cudaHostAlloc(reinterpret_cast<void **>(&h_small), 64, cudaHostAllocDefault);
-        return e;
-    }
-    void release()
-    {
-        for (int i = 0; i < 4; ++i) {
-            if (buf[i])
-                cudaFree(buf[i]);
-            buf[i] = nullptr;
-            cap[i] = 0;
-        }
-        if (h_small)
-            cudaFreeHost(h_small);
-        h_small = nullptr;
-        if (st)
-            cudaStreamDestroy(st);
-        st = nullptr;
-    }
-};
-
-static HostCtx g_ctx;
-
-static unsigned host_varint_decode(const uint8_t *p, uint64_t avail, uint64_t *out)
-{
-    uint64_t v = 0;
-    unsigned shift = 0;
-    for (unsigned k = 0; k < avail && k < 10; ++k) {
-        v |= (uint64_t)(p[k] & 0x7fu) << shift;
-        shift += 7;
-        if (!(p[k] & 0x80u)) {
-            *out = v;
-            return k + 1;
-        }
-    }
-    return 0;
-}
-
-} // namespace sb200
-
-extern "C" {
-
-int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
-                              uint64_t *out_bytes)
-{
-    if (!out_bytes || (n_bytes && (!in || !out)))
-        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
-    *out_bytes = 0;
-    if (n_bytes == 0)
-        return SNAPPY_B200_OK;
-    std::lock_guard<std::mutex> lock(g_ctx.mu);
-    cudaError_t e = g_ctx.init();
-    if (e != cudaSuccess)
-        return cuda_fail(e, "context init");
-    const uint64_t nb = (n_bytes + kBlock - 1) / kBlock;
-    const uint64_t max_out = snappy_b200_max_compressed_bytes(n_bytes);
-    const size_t ws_bytes = compress_ws_bytes(n_bytes);
-    if ((e = g_ctx.need(0, n_bytes)) != cudaSuccess || (e = g_ctx.need(1, max_out)) != cudaSuccess ||
-        (e = g_ctx.need(2, ws_bytes)) != cudaSuccess || (e = g_ctx.need(3, (nb + 1) * 8 + 64)) != cudaSuccess)
-        return cuda_fail(e, "cudaMalloc");
-    uint8_t *d_in = static_cast<uint8_t *>(g_ctx.buf[0]);
-    uint8_t *d_out = static_cast<uint8_t *>(g_ctx.buf[1]);
-    uint64_t *d_small = static_cast<uint64_t *>(g_ctx.buf[3]); // [0] out_bytes, [1] status
-    cudaStream_t st = g_ctx.st;
-    if ((e = cudaMemcpyAsync(d_in, in, n_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-        return cuda_fail(e, "H2D copy");
-    int rc = snappy_b200_compress_device(d_in, n_bytes, mode, d_out, max_out, d_small, nullptr,
-                                         reinterpret_cast<uint32_t *>(d_small + 1), g_ctx.buf[2], g_ctx.cap[2], st);
-    if (rc != SNAPPY_B200_OK)
-        return rc;
-    if ((e = cudaMemcpyAsync(g_ctx.h_small, d_small, 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-        (e = cudaStreamSynchronize(st)) != cudaSuccess)
-        return cuda_fail(e, "compress");
-    const uint64_t total = g_ctx.h_small[0];
-    const uint32_t status = (uint32_t)g_ctx.h_small[1];
-    if (status)
-        return status_to_error(status);
-    if (total > out_capacity)
-        return fail(SNAPPY_B200_ERR_CAPACITY, "compressed stream needs %llu bytes, capacity is %llu",
-                    (unsigned long long)total, (unsigned long long)out_capacity);
-    if ((e = cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-        (e = cudaStreamSynchronize(st)) != cudaSuccess)
-        return cuda_fail(e, "D2H copy");
-    *out_bytes = total;
-    return SNAPPY_B200_OK;
-}
-
-int snappy_b200_uncompressed_length(const void *stream, uint64_t stream_bytes, uint64_t *n_bytes)
-{
-    if (!n_bytes)
-        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
-    *n_bytes = 0;
-    if (stream_bytes == 0)
-        return SNAPPY_B200_OK; // the reference's empty stream
-    if (!host_varint_decode(static_cast<const uint8_t *>(stream), stream_bytes, n_bytes))
-        return fail(SNAPPY_B200_ERR_CORRUPT, "bad varint preamble");
-    return SNAPPY_B200_OK;
-}
-
-int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void *out, uint64_t out_capacity,
-                                uint64_t *out_bytes)
-{
-    if (!out_bytes || (stream_bytes && !stream))
-        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
-    *out_bytes = 0;
-    if (stream_bytes == 0)
-        return SNAPPY_B200_OK;
-    uint64_t total = 0;
-    const unsigned hdr = host_varint_decode(static_cast<const uint8_t *>(stream), stream_bytes, &total);
-    if (!hdr)
-        return fail(SNAPPY_B200_ERR_CORRUPT, "bad varint preamble");
-    if (total > out_capacity)
-        return fail(SNAPPY_B200_ERR_CAPACITY, "output needs %llu bytes, capacity is %llu", (unsigned long long)total,
-                    (unsigned long long)out_capacity);
-    if (total == 0)
-        return stream_bytes == hdr ? SNAPPY_B200_OK : fail(SNAPPY_B200_ERR_CORRUPT, "trailing bytes after empty stream");
-    if (!out)
-        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
-    std::lock_guard<std::mutex> lock(g_ctx.mu);
-    cudaError_t e = g_ctx.init();
-    if (e != cudaSuccess)
-        return cuda_fail(e, "context init");
-    const uint64_t nb = (total + kBlock - 1) / kBlock;
-    const size_t ws_bytes = index_workspace_bytes(stream_bytes);
-    if ((e = g_ctx.need(0, stream_bytes)) != cudaSuccess || (e = g_ctx.need(1, total)) != cudaSuccess ||
-        (e = g_ctx.need(2, ws_bytes)) != cudaSuccess || (e = g_ctx.need(3, (nb + 1) * 8 + 64)) != cudaSuccess)
-        return cuda_fail(e, "cudaMalloc");
-    uint8_t *d_stream = static_cast<uint8_t *>(g_ctx.buf[0]);
-    uint8_t *d_out = static_cast<uint8_t *>(g_ctx.buf[1]);
-    uint64_t *d_small = static_cast<uint64_t *>(g_ctx.buf[3]);
-    uint32_t *d_status = reinterpret_cast<uint32_t *>(d_small);
-    uint64_t *d_offsets = d_small + 2;
-    cudaStream_t st = g_ctx.st;
-    if ((e = cudaMemcpyAsync(d_stream, stream, stream_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-        (e = cudaMemsetAsync(d_small, 0, 16, st)) != cudaSuccess)
-        return cuda_fail(e, "H2D copy");
-    int rc = snappy_b200_decompress_device(d_stream, stream_bytes, hdr, total, d_out, d_offsets, d_status, g_ctx.buf[2],
-                                           g_ctx.cap[2], st);
-    if (rc != SNAPPY_B200_OK)
-        return rc;
-    if ((e = cudaMemcpyAsync(g_ctx.h_small, d_small, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-        (e = cudaStreamSynchronize(st)) != cudaSuccess)
-        return cuda_fail(e, "decompress");
-    const uint32_t status = (uint32_t)g_ctx.h_small[0];
-    if (status)
-        return status_to_error(status);
-    if ((e = cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-        (e = cudaStreamSynchronize(st)) != cudaSuccess)
-        return cuda_fail(e, "D2H copy");
-    *out_bytes = total;
-    return SNAPPY_B200_OK;
-}
-
-void snappy_b200_release(void)
-{
-    std::lock_guard<std::mutex> lock(g_ctx.mu);
-    g_ctx.release();
-}
-
-} // extern "C"

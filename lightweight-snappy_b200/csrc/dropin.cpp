@@ -6,7 +6,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <vector>
 
 #include "buffer_compression.h"
 #include "snappy_b200.h"
@@ -17,37 +16,80 @@
 
 namespace {
 
+// A growable byte buffer in page-locked host memory (plain malloc when no device is usable, so
+// that error paths still work): what the reference's Buffer / IO_utils allocations become.
+struct PinnedBuf {
+    uint8_t *p = nullptr;
+    size_t cap = 0, n = 0;
+    bool pinned = false;
+    ~PinnedBuf() { drop(); }
+    void drop()
+    {
+        if (p) {
+            if (pinned)
+                snappy_b200_host_free(p);
+            else
+                free(p);
+        }
+        p = nullptr;
+        cap = n = 0;
+    }
+    bool reserve(size_t want)
+    {
+        if (want <= cap)
+            return true;
+        void *q = snappy_b200_host_alloc(want);
+        bool qp = q != nullptr;
+        if (!q)
+            q = malloc(want);
+        if (!q)
+            return false;
+        if (n)
+            memcpy(q, p, n);
+        const size_t keep = n;
+        drop();
+        p = static_cast<uint8_t *>(q);
+        cap = want;
+        n = keep;
+        pinned = qp;
+        return true;
+    }
+    uint8_t *data() { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+};
+
 // Reads from the current position to EOF (the reference's fread loop, src/snappy_compression.c:210-213).
-bool read_all(FILE *f, uint64_t hint, std::vector<uint8_t> &buf)
+bool read_all(FILE *f, uint64_t hint, PinnedBuf &buf)
 {
-    buf.clear();
-    size_t cap = hint ? hint + 1 : (1u << 16);
-    size_t n = 0;
+    size_t cap = hint ? hint + 1 : (1u << 20);
+    buf.n = 0;
     for (;;) {
-        buf.resize(cap);
-        const size_t got = fread(buf.data() + n, 1, cap - n, f);
-        n += got;
-        if (n < cap) {
+        if (!buf.reserve(cap))
+            return false;
+        const size_t got = fread(buf.p + buf.n, 1, cap - buf.n, f);
+        buf.n += got;
+        if (buf.n < cap) {
             if (ferror(f))
                 return false;
             break;
         }
         cap *= 2;
     }
-    buf.resize(n);
     return true;
 }
 
 int compress_file(FILE *in, unsigned long long declared, FILE *out, int mode)
 {
-    std::vector<uint8_t> data;
+    PinnedBuf data, stream;
     if (!in || !out || !read_all(in, declared, data))
         return SNAPPY_B200_ERR_IO;
     if (data.empty())
         return SNAPPY_B200_OK; // reference: empty input -> empty output
-    std::vector<uint8_t> stream(snappy_b200_max_compressed_bytes(data.size()));
+    if (!stream.reserve(snappy_b200_max_compressed_bytes(data.size())))
+        return SNAPPY_B200_ERR_IO;
     uint64_t n = 0;
-    const int rc = snappy_b200_compress_host(data.data(), data.size(), mode, stream.data(), stream.size(), &n);
+    const int rc = snappy_b200_compress_host(data.data(), data.size(), mode, stream.data(), stream.cap, &n);
     if (rc != SNAPPY_B200_OK) {
         fprintf(stderr, "snappy_b200: %s\n", snappy_b200_last_error());
         return rc;
@@ -80,15 +122,16 @@ int snappy_compress_bst(FILE *file_input, unsigned long long input_size, FILE *f
 
 int snappy_decompress(FILE *file_input, FILE *file_decompressed)
 {
-    std::vector<uint8_t> stream;
+    PinnedBuf stream, out;
     if (!file_input || !file_decompressed || !read_all(file_input, 0, stream))
         return SNAPPY_B200_ERR_IO;
     uint64_t total = 0;
     int rc = snappy_b200_uncompressed_length(stream.data(), stream.size(), &total);
     if (rc == SNAPPY_B200_OK && total) {
-        std::vector<uint8_t> out(total);
+        if (!out.reserve(total))
+            return SNAPPY_B200_ERR_IO;
         uint64_t n = 0;
-        rc = snappy_b200_decompress_host(stream.data(), stream.size(), out.data(), out.size(), &n);
+        rc = snappy_b200_decompress_host(stream.data(), stream.size(), out.data(), out.cap, &n);
         if (rc == SNAPPY_B200_OK && fwrite(out.data(), 1, n, file_decompressed) != n)
             rc = SNAPPY_B200_ERR_IO;
     }

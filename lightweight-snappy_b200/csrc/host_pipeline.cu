@@ -1,0 +1,420 @@
+// host_pipeline.cu -- the host-buffer entry points (include/snappy_b200.h, layer 2): the
+// batched block scheduler that sits where the reference's Buffer / fread / fwrite loop was
+// (src/snappy_compression.c:414-428, src/snappy_decompression.c:345-363).
+//
+// The input is framed into chunks of whole 64 KiB blocks and streamed through the GPU on three
+// CUDA streams so that the upload of chunk j+1, the kernels of chunk j and the download of
+// chunk j-1 overlap (PCIe is full duplex):
+//   compress    chunk = 2048 blocks (128 MiB), four chunks in flight, each on its own stream: the
+//               parse is a latency-bound chain per block, so the GPU only fills up when
+//               thousands of blocks are resident at once.  Each chunk is compressed into bare
+//               blocks (the first one also carries the varint of the whole input); its size is
+//               read back, which tells where the chunk goes in the caller's buffer, and its
+//               bytes follow on the download stream.
+//   decompress  the stream is uploaded in 128 MiB pieces.  Whenever a piece has landed, K0 runs
+//               on the not-yet-decoded tail of what is on the device ("open-ended": the
+//               element cut off by the end of the piece is not an error); every block that is
+//               complete is decoded by the segment-driven decoder on a second stream (so it
+//               overlaps K0 of the next piece) and downloaded while later pieces are still in
+//               flight; the incomplete last block is taken up again with the next piece.
+// Host buffers may be pageable or page-locked; with page-locked buffers (cudaHostAlloc /
+// cudaHostRegister, torch pin_memory) the copies are truly asynchronous.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace sb200 {
+int fail_msg(int code, const char *msg);
+int cuda_fail_msg(cudaError_t e, const char *what);
+int status_error(uint32_t st);
+size_t compress_workspace_bytes_internal(uint64_t n_bytes);
+void add_launches(uint64_t n);
+cudaError_t compress_chunk(const uint8_t *, uint64_t, uint64_t, int, uint8_t *, uint64_t, uint64_t *, uint32_t *, void *,
+                           cudaStream_t);
+size_t index_workspace_bytes(uint64_t);
+cudaError_t run_index(const uint8_t *, uint64_t, uint64_t, uint64_t, uint64_t *, uint32_t *, void *, cudaStream_t,
+                      uint64_t *, bool, uint64_t);
+const uint4 *index_starts(void *, uint64_t);
+const uint64_t *index_total(void *, uint64_t);
+cudaError_t launch_decode_seg(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, uint64_t, uint64_t, uint8_t *,
+                              uint32_t *, cudaStream_t, uint64_t *);
+
+namespace {
+
+constexpr int kSlots = 4; // compress chunks in flight
+
+// Chunk sizes in MiB; SNAPPY_B200_CHUNK_MIB / SNAPPY_B200_PIECE_MIB override them (tests use
+// small values to exercise many chunks on small inputs).
+uint64_t env_mib(const char *name, uint64_t dflt)
+{
+    const char *v = getenv(name);
+    const long long x = v ? atoll(v) : 0;
+    return (uint64_t)(x > 0 ? x : (long long)dflt) << 20;
+}
+#define kCompressChunk env_mib("SNAPPY_B200_CHUNK_MIB", 128) /* input bytes per compress chunk (whole blocks) */
+#define kUploadPiece env_mib("SNAPPY_B200_PIECE_MIB", 128)   /* stream bytes per upload piece */
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline uint64_t max_compressed(uint64_t n)
+{
+    return n ? 10 + n + ((n + kBlock - 1) / kBlock) * 1010 : 0;
+}
+
+unsigned host_varint_decode(const uint8_t *p, uint64_t avail, uint64_t *out)
+{
+    uint64_t v = 0;
+    unsigned shift = 0;
+    for (unsigned k = 0; k < avail && k < 10; ++k) {
+        v |= (uint64_t)(p[k] & 0x7fu) << shift;
+        shift += 7;
+        if (!(p[k] & 0x80u)) {
+            *out = v;
+            return k + 1;
+        }
+    }
+    return 0;
+}
+
+// Cached per-process resources of the synchronous host-buffer entry points.
+struct HostCtx {
+    static constexpr int kBufs = 16;
+    std::mutex mu;
+    cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr, s_dec = nullptr;
+    cudaStream_t s_slot[kSlots] = {};
+    void *buf[kBufs] = {};
+    size_t cap[kBufs] = {};
+    uint64_t *h_small = nullptr; // pinned scratch for small read-backs
+    cudaEvent_t ev[32] = {};
+
+    cudaError_t need(int i, size_t bytes)
+    {
+        bytes = align_up(bytes + 256, 1 << 20);
+        if (cap[i] >= bytes)
+            return cudaSuccess;
+        if (buf[i])
+            cudaFree(buf[i]);
+        buf[i] = nullptr;
+        cap[i] = 0;
+        cudaError_t e = cudaMalloc(&buf[i], bytes);
+        if (e == cudaSuccess)
+            cap[i] = bytes;
+        return e;
+    }
+    cudaError_t init()
+    {
+        cudaError_t e = cudaSuccess;
+        for (cudaStream_t *s : {&s_up, &s_run, &s_down, &s_dec, &s_slot[0], &s_slot[1], &s_slot[2], &s_slot[3]})
+            if (e == cudaSuccess && !*s)
+                e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+        if (e == cudaSuccess && !h_small)
+            e = cudaHostAlloc(reinterpret_cast<void **>(&h_small), 256, cudaHostAllocDefault);
+        for (auto &x : ev)
+            if (e == cudaSuccess && !x)
+                e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+        return e;
+    }
+    void release()
+    {
+        for (int i = 0; i < kBufs; ++i) {
+            if (buf[i])
+                cudaFree(buf[i]);
+            buf[i] = nullptr;
+            cap[i] = 0;
+        }
+        if (h_small)
+            cudaFreeHost(h_small);
+        h_small = nullptr;
+        for (auto &x : ev) {
+            if (x)
+                cudaEventDestroy(x);
+            x = nullptr;
+        }
+        for (cudaStream_t *s : {&s_up, &s_run, &s_down, &s_dec, &s_slot[0], &s_slot[1], &s_slot[2], &s_slot[3]}) {
+            if (*s)
+                cudaStreamDestroy(*s);
+            *s = nullptr;
+        }
+    }
+};
+
+HostCtx g_ctx;
+
+#define CU(call, what)                                                                                                 \
+    do {                                                                                                               \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess) {                                                                                      \
+            cudaDeviceSynchronize();                                                                                   \
+            return cuda_fail_msg(e__, what);                                                                           \
+        }                                                                                                              \
+    } while (0)
+
+} // namespace
+} // namespace sb200
+
+using namespace sb200;
+
+extern "C" {
+
+int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
+                              uint64_t *out_bytes)
+{
+    if (!out_bytes || (n_bytes && (!in || !out)))
+        return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    if (mode != SNAPPY_B200_MODE_HASH && mode != SNAPPY_B200_MODE_BST)
+        return fail_msg(SNAPPY_B200_ERR_ARG, "unknown mode");
+    *out_bytes = 0;
+    if (n_bytes == 0)
+        return SNAPPY_B200_OK; // reference: an empty input gives an empty stream
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    CU(g_ctx.init(), "context init");
+    const uint64_t chunk = std::min<uint64_t>(kCompressChunk, align_up(n_bytes, kBlock));
+    const uint64_t n_chunks = (n_bytes + chunk - 1) / chunk;
+    const uint64_t out_cap_chunk = max_compressed(chunk);
+    const size_t ws_bytes = compress_workspace_bytes_internal(chunk);
+    const int slots = (int)std::min<uint64_t>(kSlots, n_chunks);
+    // buffers: s input, 4+s output, 8+s workspace, 12 small
+    for (int s = 0; s < slots; ++s) {
+        CU(g_ctx.need(0 + s, chunk), "cudaMalloc");
+        CU(g_ctx.need(4 + s, out_cap_chunk), "cudaMalloc");
+        CU(g_ctx.need(8 + s, ws_bytes), "cudaMalloc");
+    }
+    CU(g_ctx.need(12, 256), "cudaMalloc");
+    uint64_t *d_small = static_cast<uint64_t *>(g_ctx.buf[12]); // per slot: [4s] out_bytes, [4s+1] status
+    cudaEvent_t *ev_up = g_ctx.ev, *ev_run = g_ctx.ev + 4, *ev_down = g_ctx.ev + 8, *ev_size = g_ctx.ev + 12;
+    const uint8_t *src = static_cast<const uint8_t *>(in);
+    uint8_t *dst = static_cast<uint8_t *>(out);
+
+    // Enqueues everything chunk j needs up to (and including) the read-back of its size.
+    auto issue = [&](uint64_t j) -> cudaError_t {
+        const int s = (int)(j % slots);
+        const uint64_t lo = j * chunk, len = std::min(chunk, n_bytes - lo);
+        cudaStream_t st = g_ctx.s_slot[s];
+        cudaError_t e = cudaSuccess;
+        if (j >= (uint64_t)slots) // the kernels of the previous user of this slot are done with its input
+            e = cudaStreamWaitEvent(g_ctx.s_up, ev_run[s], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(g_ctx.buf[0 + s], src + lo, len, cudaMemcpyHostToDevice, g_ctx.s_up);
+        if (e == cudaSuccess)
+            e = cudaEventRecord(ev_up[s], g_ctx.s_up);
+        if (e == cudaSuccess)
+            e = cudaStreamWaitEvent(st, ev_up[s], 0);
+        if (e == cudaSuccess && j >= (uint64_t)slots) // ... and its download has left the output buffer
+            e = cudaStreamWaitEvent(st, ev_down[s], 0);
+        uint64_t *d_bytes = d_small + 4 * s;
+        uint32_t *d_status = reinterpret_cast<uint32_t *>(d_small + 4 * s + 1);
+        if (e == cudaSuccess)
+            e = cudaMemsetAsync(d_bytes, 0, 16, st);
+        if (e == cudaSuccess)
+            e = compress_chunk(static_cast<const uint8_t *>(g_ctx.buf[0 + s]), len, j == 0 ? n_bytes : 0, mode,
+                               static_cast<uint8_t *>(g_ctx.buf[4 + s]), out_cap_chunk, d_bytes, d_status,
+                               g_ctx.buf[8 + s], st);
+        if (e == cudaSuccess)
+            e = cudaEventRecord(ev_run[s], st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(g_ctx.h_small + 4 * s, d_bytes, 16, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+            e = cudaEventRecord(ev_size[s], st);
+        return e;
+    };
+
+    uint64_t off = 0, issued = 0;
+    for (uint64_t j = 0; j < n_chunks; ++j) {
+        while (issued < n_chunks && issued < j + (uint64_t)slots)
+            CU(issue(issued++), "compress launch");
+        const int s = (int)(j % slots);
+        CU(cudaEventSynchronize(ev_size[s]), "compress");
+        const uint64_t clen = g_ctx.h_small[4 * s];
+        const uint32_t status = (uint32_t)g_ctx.h_small[4 * s + 1];
+        if (status) {
+            cudaDeviceSynchronize();
+            return status_error(status);
+        }
+        if (off + clen > out_capacity) {
+            cudaDeviceSynchronize();
+            return fail_msg(SNAPPY_B200_ERR_CAPACITY, "output buffer too small for the compressed stream");
+        }
+        CU(cudaStreamWaitEvent(g_ctx.s_down, ev_run[s], 0), "stream wait");
+        CU(cudaMemcpyAsync(dst + off, g_ctx.buf[4 + s], clen, cudaMemcpyDeviceToHost, g_ctx.s_down), "D2H copy");
+        CU(cudaEventRecord(ev_down[s], g_ctx.s_down), "event record");
+        off += clen;
+    }
+    CU(cudaStreamSynchronize(g_ctx.s_down), "D2H copy");
+    *out_bytes = off;
+    return SNAPPY_B200_OK;
+}
+
+int snappy_b200_uncompressed_length(const void *stream, uint64_t stream_bytes, uint64_t *n_bytes)
+{
+    if (!n_bytes)
+        return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    *n_bytes = 0;
+    if (stream_bytes == 0)
+        return SNAPPY_B200_OK; // the reference's empty stream
+    if (!host_varint_decode(static_cast<const uint8_t *>(stream), stream_bytes, n_bytes))
+        return fail_msg(SNAPPY_B200_ERR_CORRUPT, "bad varint preamble");
+    return SNAPPY_B200_OK;
+}
+
+int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void *out, uint64_t out_capacity,
+                                uint64_t *out_bytes)
+{
+    if (!out_bytes || (stream_bytes && !stream))
+        return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    *out_bytes = 0;
+    if (stream_bytes == 0)
+        return SNAPPY_B200_OK;
+    uint64_t total = 0;
+    const unsigned hdr = host_varint_decode(static_cast<const uint8_t *>(stream), stream_bytes, &total);
+    if (!hdr)
+        return fail_msg(SNAPPY_B200_ERR_CORRUPT, "bad varint preamble");
+    if (total > out_capacity)
+        return fail_msg(SNAPPY_B200_ERR_CAPACITY, "output buffer too small for the decompressed data");
+    if (total == 0)
+        return stream_bytes == hdr ? SNAPPY_B200_OK
+                                   : fail_msg(SNAPPY_B200_ERR_CORRUPT, "trailing bytes after an empty stream");
+    if (!out)
+        return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    if (stream_bytes > max_compressed(total) + 16)
+        return fail_msg(SNAPPY_B200_ERR_CORRUPT, "stream is longer than any encoding of its declared length");
+
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    CU(g_ctx.init(), "context init");
+    const uint64_t nb = (total + kBlock - 1) / kBlock;
+    const uint64_t piece = kUploadPiece;
+    const uint64_t n_pieces = (stream_bytes + piece - 1) / piece;
+    // a K0 region is at most one piece plus the carried-over incomplete block
+    const uint64_t region_cap = std::min<uint64_t>(stream_bytes, piece + 2 * (uint64_t)kBlock + 4096);
+    // buffers: 0 stream, 1 output, 2/3 K0 workspace (alternating), 4/5 block offsets, 6 small
+    CU(g_ctx.need(0, stream_bytes + 64), "cudaMalloc");
+    CU(g_ctx.need(1, total), "cudaMalloc");
+    for (int s = 0; s < 2; ++s) {
+        CU(g_ctx.need(2 + s, index_workspace_bytes(region_cap)), "cudaMalloc");
+        CU(g_ctx.need(4 + s, (nb + 2) * 8), "cudaMalloc");
+    }
+    CU(g_ctx.need(6, 256), "cudaMalloc");
+    uint8_t *d_stream = static_cast<uint8_t *>(g_ctx.buf[0]);
+    uint8_t *d_out = static_cast<uint8_t *>(g_ctx.buf[1]);
+    uint32_t *d_status = static_cast<uint32_t *>(g_ctx.buf[6]);
+    const uint8_t *src = static_cast<const uint8_t *>(stream);
+    uint8_t *dst = static_cast<uint8_t *>(out);
+    cudaEvent_t *ev_up = g_ctx.ev;          // 8, round robin
+    cudaEvent_t *ev_k0 = g_ctx.ev + 8;      // 2: K0 of a piece finished (its maps are ready)
+    cudaEvent_t *ev_dec = g_ctx.ev + 10;    // 2: decode of a piece finished (its workspace is free)
+
+    CU(cudaMemsetAsync(d_status, 0, 4, g_ctx.s_run), "memset");
+    uint64_t issued = 0; // pieces whose upload has been enqueued (at most 8 ahead of the consumer)
+    auto issue_upload = [&]() -> cudaError_t {
+        const uint64_t q = issued++;
+        const uint64_t lo = q * piece, len = std::min(piece, stream_bytes - lo);
+        cudaError_t e = cudaMemcpyAsync(d_stream + lo, src + lo, len, cudaMemcpyHostToDevice, g_ctx.s_up);
+        if (e == cudaSuccess)
+            e = cudaEventRecord(ev_up[q & 7], g_ctx.s_up);
+        return e;
+    };
+    while (issued < n_pieces && issued < 8)
+        CU(issue_upload(), "H2D copy");
+
+    uint64_t rs = hdr; // stream offset of the first block that is not decoded yet
+    uint64_t ob = 0;   // blocks decoded so far
+    uint64_t launches = 0, rounds_used = 0;
+    for (uint64_t p = 0; p < n_pieces; ++p) {
+        const bool last = p + 1 == n_pieces;
+        const uint64_t hi = std::min((p + 1) * piece, stream_bytes);
+        CU(cudaStreamWaitEvent(g_ctx.s_run, ev_up[p & 7], 0), "stream wait");
+        if (issued < n_pieces) // keep the upload queue full (the event slot of piece p is free again)
+            CU(issue_upload(), "H2D copy");
+        if (hi <= rs)
+            continue;
+        const uint64_t region = hi - rs;
+        if (region > region_cap) {
+            cudaDeviceSynchronize();
+            return fail_msg(SNAPPY_B200_ERR_FRAMING, "a block of the stream is larger than any 64 KiB block can be");
+        }
+        const int s = (int)(rounds_used & 1);
+        void *ws = g_ctx.buf[2 + s];
+        uint64_t *d_offsets = static_cast<uint64_t *>(g_ctx.buf[4 + s]);
+        if (rounds_used >= 2) // the decode that last read this workspace must be done
+            CU(cudaStreamWaitEvent(g_ctx.s_run, ev_dec[s], 0), "stream wait");
+        const uint64_t blocks_left = nb - ob;
+        const uint64_t out_left = total - ob * kBlock;
+        // K0 on the not-yet-decoded tail; offsets come out relative to d_stream + rs
+        CU(run_index(d_stream + rs, region, 0, last ? out_left : 0, d_offsets, d_status, ws, g_ctx.s_run, &launches,
+                     !last, blocks_left),
+           "index launch");
+        CU(cudaEventRecord(ev_k0[s], g_ctx.s_run), "event record");
+        CU(cudaMemcpyAsync(g_ctx.h_small, index_total(ws, region), 8, cudaMemcpyDeviceToHost, g_ctx.s_run), "read-back");
+        CU(cudaMemcpyAsync(g_ctx.h_small + 1, d_status, 4, cudaMemcpyDeviceToHost, g_ctx.s_run), "read-back");
+        CU(cudaStreamSynchronize(g_ctx.s_run), "index");
+        const uint32_t status = (uint32_t)g_ctx.h_small[1];
+        if (status) {
+            cudaDeviceSynchronize();
+            return status_error(status);
+        }
+        const uint64_t produced = g_ctx.h_small[0];
+        // complete blocks: all of their elements are on the device and the start of the next
+        // block is known (it is an element start inside the region)
+        uint64_t kdone = last ? blocks_left : produced / kBlock;
+        if (!last && kdone > 0 && produced == kdone * kBlock)
+            --kdone; // the start of block kdone may lie just beyond the region: wait for more bytes
+        if (kdone > blocks_left)
+            kdone = blocks_left;
+        if (kdone == 0)
+            continue;
+        ++rounds_used;
+        const uint64_t out_bytes_now = last ? out_left : kdone * kBlock;
+        CU(cudaMemcpyAsync(g_ctx.h_small + 2, d_offsets + kdone, 8, cudaMemcpyDeviceToHost, g_ctx.s_run), "read-back");
+        // decode on its own stream: K0 of the next piece does not wait for it
+        CU(cudaStreamWaitEvent(g_ctx.s_dec, ev_k0[s], 0), "stream wait");
+        CU(launch_decode_seg(d_stream + rs, 0, d_offsets, index_starts(ws, region), kdone, out_bytes_now,
+                             d_out + ob * kBlock, d_status, g_ctx.s_dec, &launches),
+           "decode launch");
+        CU(cudaEventRecord(ev_dec[s], g_ctx.s_dec), "event record");
+        CU(cudaStreamWaitEvent(g_ctx.s_down, ev_dec[s], 0), "stream wait");
+        CU(cudaMemcpyAsync(dst + ob * kBlock, d_out + ob * kBlock, out_bytes_now, cudaMemcpyDeviceToHost, g_ctx.s_down),
+           "D2H copy");
+        CU(cudaStreamSynchronize(g_ctx.s_run), "read-back");
+        rs += g_ctx.h_small[2];
+        ob += kdone;
+    }
+    add_launches(launches);
+    CU(cudaStreamSynchronize(g_ctx.s_dec), "decode");
+    CU(cudaMemcpyAsync(g_ctx.h_small + 1, d_status, 4, cudaMemcpyDeviceToHost, g_ctx.s_run), "read-back");
+    CU(cudaStreamSynchronize(g_ctx.s_run), "decode");
+    CU(cudaStreamSynchronize(g_ctx.s_down), "D2H copy");
+    const uint32_t status = (uint32_t)g_ctx.h_small[1];
+    if (status)
+        return status_error(status);
+    if (ob != nb)
+        return fail_msg(SNAPPY_B200_ERR_CORRUPT, "the stream ends before its declared length is reached");
+    *out_bytes = total;
+    return SNAPPY_B200_OK;
+}
+
+void *snappy_b200_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void snappy_b200_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
+void snappy_b200_release(void)
+{
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    g_ctx.release();
+}
+
+} // extern "C"

@@ -427,7 +427,8 @@ __global__ void __launch_bounds__(kGroupCta) k_group_final(const uint8_t *__rest
 // map by the exact map of element starts -- what the segment-driven decoder consumes.
 __global__ void __launch_bounds__(256) k_index_outlen(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
                                                       const uint8_t *__restrict__ entry, uint64_t *__restrict__ outlen,
-                                                      uint4 *__restrict__ starts, uint32_t *__restrict__ status)
+                                                      uint4 *__restrict__ starts, uint32_t *__restrict__ status,
+                                                      int open_end)
 {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t >= nseg)
@@ -442,7 +443,10 @@ __global__ void __launch_bounds__(256) k_index_outlen(const uint8_t *__restrict_
         while (e < hi) {
             const Elem el = decode_at(body, body_len, e);
             if (!el.ok || e + el.size > body_len) {
-                atomicOr(status, SNAPPY_B200_ST_CORRUPT);
+                // the element runs past the bytes we have: an error for a whole stream, the
+                // normal end of a partial one (open_end: the rest has not been uploaded yet)
+                if (!open_end)
+                    atomicOr(status, SNAPPY_B200_ST_CORRUPT);
                 break;
             }
             if (el.out > kBlock)
@@ -578,14 +582,14 @@ __global__ void __launch_bounds__(256) k_index_blocks(const uint8_t *__restrict_
     uint64_t e = lo + en, op = outoff[t];
     while (e < hi) {
         const Elem el = decode_at(body, body_len, e);
-        if (!el.ok || e + el.size > body_len)
-            break; // already flagged by k_index_outlen
         const uint64_t within = op & (kBlock - 1);
-        if (within == 0) {
+        if (within == 0) { // e is a true element start even if the element itself is cut off
             const uint64_t bi = op / kBlock;
             if (bi < n_blocks)
                 block_offsets[bi] = body_offset + e;
         }
+        if (!el.ok || e + el.size > body_len)
+            break; // already flagged by k_index_outlen (or the open end of a partial stream)
         if (within + el.out > kBlock)
             atomicOr(status, SNAPPY_B200_ST_FRAMING);
         op += el.out;
@@ -594,9 +598,10 @@ __global__ void __launch_bounds__(256) k_index_blocks(const uint8_t *__restrict_
 }
 
 __global__ void k_index_finish(const uint64_t *__restrict__ total, uint64_t total_out, uint64_t stream_bytes,
-                               uint64_t n_blocks, uint64_t *__restrict__ block_offsets, uint32_t *__restrict__ status)
+                               uint64_t n_blocks, uint64_t *__restrict__ block_offsets, uint32_t *__restrict__ status,
+                               int open_end)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !open_end) {
         block_offsets[n_blocks] = stream_bytes;
         if (*total != total_out)
             atomicOr(status, SNAPPY_B200_ST_CORRUPT);
@@ -665,19 +670,28 @@ static uint64_t g_last_rounds = 0;
 uint64_t index_last_rounds() { return g_last_rounds; }
 
 // Synchronises the stream between relaxation rounds (it has to read the "changed" flag).
+// The total output length the last run_index counted (device scalar in the workspace).
+const uint64_t *index_total(void *d_ws, uint64_t stream_bytes) { return carve(d_ws, stream_bytes).total; }
+
+// open_end: the bytes are the beginning of a longer stream (the host pipeline decodes while the
+// rest is still being uploaded).  The element cut off by the end is not an error then, the
+// total is not checked, and at most n_blocks_cap block starts are recorded.
 cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset, uint64_t total_out,
-                      uint64_t *d_block_offsets, uint32_t *d_status, void *d_ws, cudaStream_t st, uint64_t *launches)
+                      uint64_t *d_block_offsets, uint32_t *d_status, void *d_ws, cudaStream_t st, uint64_t *launches,
+                      bool open_end, uint64_t n_blocks_cap)
 {
-    const uint64_t n_blocks = (total_out + kBlock - 1) / kBlock;
+    const uint64_t n_blocks = open_end ? n_blocks_cap : (total_out + kBlock - 1) / kBlock;
     const uint64_t body_len = stream_bytes - body_offset;
     const uint8_t *body = d_stream + body_offset;
     const uint64_t nseg = (body_len + kSeg - 1) / kSeg;
     IndexWorkspace w = carve(d_ws, stream_bytes);
     cudaError_t e;
     if (nseg == 0) {
-        k_index_finish<<<1, 32, 0, st>>>(w.total, total_out, stream_bytes, n_blocks, d_block_offsets, d_status);
+        if ((e = cudaMemsetAsync(w.total, 0, 8, st)) != cudaSuccess)
+            return e;
+        k_index_finish<<<1, 32, 0, st>>>(w.total, total_out, stream_bytes, n_blocks, d_block_offsets, d_status,
+                                         open_end);
         *launches += 1;
-        // total is uninitialised here; an empty body is only legal for total_out == 0
         return cudaGetLastError();
     }
     const unsigned grid = (unsigned)((nseg + 255) / 256);
@@ -720,14 +734,14 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
     }
     k_group_final<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.entry);
     *launches += 1;
-    k_index_outlen<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outlen, w.paths, d_status);
+    k_index_outlen<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outlen, w.paths, d_status, open_end);
     const uint64_t ntile = (nseg + kScanTile - 1) / kScanTile;
     k_scan_tile_sums<<<(unsigned)ntile, kScanCta, 0, st>>>(w.outlen, nseg, w.tile_sums);
     k_scan_tiles<<<1, kScanCta, 0, st>>>(w.tile_sums, ntile, w.total);
     k_scan_apply<<<(unsigned)ntile, kScanCta, 0, st>>>(w.outlen, nseg, w.tile_sums, w.outoff);
     k_index_blocks<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outoff, body_offset, n_blocks,
                                          d_block_offsets, d_status);
-    k_index_finish<<<1, 32, 0, st>>>(w.total, total_out, stream_bytes, n_blocks, d_block_offsets, d_status);
+    k_index_finish<<<1, 32, 0, st>>>(w.total, total_out, stream_bytes, n_blocks, d_block_offsets, d_status, open_end);
     *launches += 6;
     return cudaGetLastError();
 }

@@ -169,6 +169,33 @@ def test_roundtrip_properties_at_scale():
     assert 1.5 < ratio < 4.0, ratio
 
 
+def test_host_pipeline_many_chunks(monkeypatch):
+    """The chunked host pipeline (3 compress chunks, 4 upload pieces, a ragged tail) gives the
+    same stream as one device-resident call, from pageable and from page-locked buffers."""
+    import torch
+    monkeypatch.setenv("SNAPPY_B200_CHUNK_MIB", "16")   # 13 compress chunks, 4 in flight
+    monkeypatch.setenv("SNAPPY_B200_PIECE_MIB", "8")    # ~15 upload pieces
+    n = (200 << 20) + 12345
+    data = corpus.make_corpus("mixed", n, device="cuda", first_segment=7)
+    codec = api.DeviceCodec(n)
+    codec.compress(data, 0)
+    want = codec.result_stream().cpu().numpy()
+    host = data.cpu()
+    pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    pinned.copy_(host)
+    for src in (host.numpy(), pinned.numpy()):
+        got = api.compress_host(src, api.MODE_HASH)
+        _assert_same(got, want, "host pipeline stream")
+    back = api.decompress_host(want)
+    _assert_same(back, host.numpy(), "host pipeline decode")
+    out_pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    back2 = api.decompress_host(want, out=out_pinned.numpy())
+    assert back2.size == n and torch.equal(out_pinned, host)
+    # a stream cut short must be rejected, not mis-decoded
+    with pytest.raises(api.SnappyError):
+        api.decompress_host(want[: want.size - 70000])
+
+
 def test_cli_roundtrip(tmp_path, oracle):
     import subprocess
     data = datasets.gen("corpus:mixed:0:900000:400000")

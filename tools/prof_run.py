@@ -15,8 +15,12 @@ data = corpus.make_corpus(a.kind, n, device="cuda")
 codec = api.DeviceCodec(n)
 out = torch.empty(n, dtype=torch.uint8, device="cuda")
 for _ in range(a.reps):
+    ec = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ec[0].record()
     codec.compress(data, a.mode)
+    ec[1].record()
     s = codec.result_stream()
+    t_comp = ec[0].elapsed_time(ec[1])
     hdr = 1
     while (n >> (7 * hdr)) > 0:
         hdr += 1
@@ -35,6 +39,6 @@ for _ in range(a.reps):
     ev[4].record()
     codec.check_status()
     assert torch.equal(out, data)
-    print(f"{a.kind} {a.mib} MiB mode {a.mode}: ratio {n / s.numel():.3f}, K0 rounds {api.index_rounds()}, "
+    print(f"{a.kind} {a.mib} MiB mode {a.mode}: compress {t_comp:.3f} ms, ratio {n / s.numel():.3f}, K0 rounds {api.index_rounds()}, "
           f"index {ev[0].elapsed_time(ev[1]):.3f} ms, window decode {ev[1].elapsed_time(ev[2]):.3f} ms, "
           f"index+segment decode {ev[3].elapsed_time(ev[4]):.3f} ms")
