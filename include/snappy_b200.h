@@ -115,10 +115,12 @@ int snappy_b200_decode_segments_device(const uint8_t *d_stream, uint64_t stream_
                                        uint32_t *d_status, void *d_workspace, size_t workspace_bytes,
                                        void *stream);
 
-/* Decodes an index-less stream: snappy_b200_index_device followed by the segment-driven
- * decoder, which uses the element maps K0 leaves in the workspace.  d_block_offsets
- * [n_blocks+1] is filled as a by-product.  Workspace: snappy_b200_index_workspace_bytes.
- * Synchronises the stream between K0 rounds; the decode itself is only enqueued.           */
+/* Decodes an index-less stream: K0 followed by the segment-driven decoder (the decode kernel
+ * runs on a library-owned second stream that is joined back into `stream` before the call
+ * returns).  d_block_offsets [n_blocks+1] (optional) is filled as a by-product.
+ * Workspace: snappy_b200_decompress_workspace_bytes.  Synchronises `stream` between K0
+ * rounds; the last decode is only enqueued.                                                */
+size_t snappy_b200_decompress_workspace_bytes(uint64_t stream_bytes, uint64_t total_out);
 int snappy_b200_decompress_device(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
                                   uint64_t total_out, uint8_t *d_out, uint64_t *d_block_offsets,
                                   uint32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream);

@@ -49,6 +49,7 @@ SIGNATURES = {
                                            C.c_void_p]),
     "snappy_b200_decode_segments_device": (C.c_int, [_u8p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u8p, _u8p, _u8p,
                                                      C.c_size_t, C.c_void_p]),
+    "snappy_b200_decompress_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_uint64]),
     "snappy_b200_decompress_device": (C.c_int, [_u8p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u8p, _u8p, _u8p,
                                                 C.c_size_t, C.c_void_p]),
     "snappy_b200_compress_host": (C.c_int, [_u8p, C.c_uint64, C.c_int, _u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
@@ -181,7 +182,8 @@ class DeviceCodec:
         L = lib()
         self.comp_capacity = max(int(L.snappy_b200_max_compressed_bytes(max_bytes)), 16)
         ws = max(int(L.snappy_b200_compress_workspace_bytes(max_bytes, MODE_BST)),
-                 int(L.snappy_b200_index_workspace_bytes(self.comp_capacity)))
+                 int(L.snappy_b200_index_workspace_bytes(self.comp_capacity)),
+                 int(L.snappy_b200_decompress_workspace_bytes(self.comp_capacity, max_bytes)))
         self.workspace = torch.empty(ws + 256, dtype=torch.uint8, device=self.device)
         self.stream_buf = torch.empty(self.comp_capacity + 256, dtype=torch.uint8, device=self.device)
         self.block_offsets = torch.zeros(nb + 1, dtype=torch.int64, device=self.device)

@@ -233,17 +233,5 @@ int snappy_b200_decode_segments_device(const uint8_t *d_stream, uint64_t stream_
     return SNAPPY_B200_OK;
 }
 
-int snappy_b200_decompress_device(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
-                                  uint64_t total_out, uint8_t *d_out, uint64_t *d_block_offsets, uint32_t *d_status,
-                                  void *d_workspace, size_t workspace_bytes, void *stream)
-{
-    int rc = snappy_b200_index_device(d_stream, stream_bytes, body_offset, total_out, d_block_offsets, d_status,
-                                      d_workspace, workspace_bytes, stream);
-    if (rc != SNAPPY_B200_OK)
-        return rc;
-    return snappy_b200_decode_segments_device(d_stream, stream_bytes, body_offset, total_out, d_out, d_block_offsets,
-                                              d_status, d_workspace, workspace_bytes, stream);
-}
-
 } // extern "C"
 

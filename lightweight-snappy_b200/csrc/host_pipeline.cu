@@ -11,7 +11,7 @@
 //               blocks (the first one also carries the varint of the whole input); its size is
 //               read back, which tells where the chunk goes in the caller's buffer, and its
 //               bytes follow on the download stream.
-//   decompress  the stream is uploaded in 128 MiB pieces.  Whenever a piece has landed, K0 runs
+//   decompress  the stream is uploaded in 192 MiB pieces.  Whenever a piece has landed, K0 runs
 //               on the not-yet-decoded tail of what is on the device ("open-ended": the
 //               element cut off by the end of the piece is not an error); every block that is
 //               complete is decoded by the segment-driven decoder on a second stream (so it
@@ -20,6 +20,7 @@
 // Host buffers may be pageable or page-locked; with page-locked buffers (cudaHostAlloc /
 // cudaHostRegister, torch pin_memory) the copies are truly asynchronous.
 #include <algorithm>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -56,7 +57,7 @@ uint64_t env_mib(const char *name, uint64_t dflt)
     return (uint64_t)(x > 0 ? x : (long long)dflt) << 20;
 }
 #define kCompressChunk env_mib("SNAPPY_B200_CHUNK_MIB", 128) /* input bytes per compress chunk (whole blocks) */
-#define kUploadPiece env_mib("SNAPPY_B200_PIECE_MIB", 128)   /* stream bytes per upload piece */
+#define kUploadPiece env_mib("SNAPPY_B200_PIECE_MIB", 192)   /* stream bytes per upload piece (host path) */
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -143,6 +144,128 @@ struct HostCtx {
 };
 
 HostCtx g_ctx;
+
+// Adds `add` to n offsets (K0 reports them relative to the region it was given).
+__global__ void k_rebase_offsets(uint64_t *__restrict__ dst, const uint64_t *__restrict__ src, uint64_t n, uint64_t add)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = src[i] + add;
+}
+
+struct PieceHooks {
+    // enqueue on s_run whatever makes stream bytes of piece p resident (host path: wait for its upload)
+    std::function<cudaError_t(uint64_t p, cudaStream_t s_run)> before_piece;
+    // output bytes [first, first + bytes) are final once `done` (recorded on the decode stream) fires
+    std::function<cudaError_t(uint64_t first, uint64_t bytes, cudaEvent_t done)> after_decode;
+};
+
+struct PieceResources {
+    void *ws[2];           // K0 workspaces, index_workspace_bytes(region_cap) each
+    uint64_t *offs[2];     // region-relative block offsets, blocks + 2 entries each
+    cudaStream_t s_run, s_dec;
+    cudaEvent_t ev_k0[2], ev_dec[2];
+    uint64_t *h_small;     // pinned, >= 4 words
+};
+
+uint64_t piece_region_cap(uint64_t stream_bytes, uint64_t piece)
+{
+    return std::min<uint64_t>(stream_bytes, piece + 2 * (uint64_t)kBlock + 4096);
+}
+
+// Decodes a device-resident stream piece by piece: K0 on the not-yet-decoded tail of pieces
+// 0..p ("open-ended" except for the last piece), then the segment-driven decoder for every
+// block that is complete, on a second stream so that it overlaps K0 of the next piece.
+// Returns a SNAPPY_B200_* code; the last decode may still be in flight on r.s_dec.
+int decode_pieces(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t hdr, uint64_t total, uint8_t *d_out,
+                  uint64_t *d_abs_offsets, uint32_t *d_status, uint64_t piece, const PieceResources &r,
+                  const PieceHooks &hooks)
+{
+#define CUP(call, what)                                                                                                \
+    do {                                                                                                               \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess) {                                                                                      \
+            cudaDeviceSynchronize();                                                                                   \
+            add_launches(launches);                                                                                    \
+            return cuda_fail_msg(e__, what);                                                                           \
+        }                                                                                                              \
+    } while (0)
+    const uint64_t nb = (total + kBlock - 1) / kBlock;
+    const uint64_t n_pieces = (stream_bytes + piece - 1) / piece;
+    const uint64_t region_cap = piece_region_cap(stream_bytes, piece);
+    uint64_t rs = hdr; // stream offset of the first block that is not decoded yet
+    uint64_t ob = 0;   // blocks decoded so far
+    uint64_t launches = 0, used = 0;
+    for (uint64_t p = 0; p < n_pieces; ++p) {
+        const bool last = p + 1 == n_pieces;
+        const uint64_t hi = std::min((p + 1) * piece, stream_bytes);
+        if (hooks.before_piece)
+            CUP(hooks.before_piece(p, r.s_run), "stream wait");
+        if (hi <= rs)
+            continue;
+        const uint64_t region = hi - rs;
+        if (region > region_cap) {
+            cudaDeviceSynchronize();
+            add_launches(launches);
+            return fail_msg(SNAPPY_B200_ERR_FRAMING, "a block of the stream is larger than any 64 KiB block can be");
+        }
+        const int s = (int)(used & 1);
+        if (used >= 2) // the decode that last read this workspace must be done
+            CUP(cudaStreamWaitEvent(r.s_run, r.ev_dec[s], 0), "stream wait");
+        const uint64_t blocks_left = nb - ob;
+        const uint64_t out_left = total - ob * kBlock;
+        // K0 on the not-yet-decoded tail; offsets come out relative to d_stream + rs
+        CUP(run_index(d_stream + rs, region, 0, last ? out_left : 0, r.offs[s], d_status, r.ws[s], r.s_run, &launches,
+                      !last, blocks_left),
+            "index launch");
+        CUP(cudaEventRecord(r.ev_k0[s], r.s_run), "event record");
+        CUP(cudaMemcpyAsync(r.h_small, index_total(r.ws[s], region), 8, cudaMemcpyDeviceToHost, r.s_run), "read-back");
+        CUP(cudaMemcpyAsync(r.h_small + 1, d_status, 4, cudaMemcpyDeviceToHost, r.s_run), "read-back");
+        CUP(cudaStreamSynchronize(r.s_run), "index");
+        const uint32_t status = (uint32_t)r.h_small[1];
+        if (status) {
+            cudaDeviceSynchronize();
+            add_launches(launches);
+            return status_error(status);
+        }
+        const uint64_t produced = r.h_small[0];
+        // complete blocks: all of their elements are on the device and the start of the next
+        // block is known (it is an element start inside the region)
+        uint64_t kdone = last ? blocks_left : produced / kBlock;
+        if (!last && kdone > 0 && produced == kdone * kBlock)
+            --kdone; // the start of block kdone may lie just beyond the region: wait for more bytes
+        if (kdone > blocks_left)
+            kdone = blocks_left;
+        if (kdone == 0)
+            continue;
+        ++used;
+        const uint64_t out_bytes_now = last ? out_left : kdone * kBlock;
+        CUP(cudaMemcpyAsync(r.h_small + 2, r.offs[s] + kdone, 8, cudaMemcpyDeviceToHost, r.s_run), "read-back");
+        if (d_abs_offsets) {
+            k_rebase_offsets<<<(unsigned)((kdone + 1 + 255) / 256), 256, 0, r.s_run>>>(d_abs_offsets + ob, r.offs[s],
+                                                                                      kdone + 1, rs);
+            ++launches;
+        }
+        // decode on its own stream: K0 of the next piece does not wait for it
+        CUP(cudaStreamWaitEvent(r.s_dec, r.ev_k0[s], 0), "stream wait");
+        CUP(launch_decode_seg(d_stream + rs, 0, r.offs[s], index_starts(r.ws[s], region), kdone, out_bytes_now,
+                              d_out + ob * kBlock, d_status, r.s_dec, &launches),
+            "decode launch");
+        CUP(cudaEventRecord(r.ev_dec[s], r.s_dec), "event record");
+        if (hooks.after_decode)
+            CUP(hooks.after_decode(ob * kBlock, out_bytes_now, r.ev_dec[s]), "D2H copy");
+        CUP(cudaStreamSynchronize(r.s_run), "read-back");
+        rs += r.h_small[2];
+        ob += kdone;
+    }
+    add_launches(launches);
+    if (ob != nb) {
+        cudaDeviceSynchronize();
+        return fail_msg(SNAPPY_B200_ERR_CORRUPT, "the stream ends before its declared length is reached");
+    }
+    return SNAPPY_B200_OK;
+#undef CUP
+}
 
 #define CU(call, what)                                                                                                 \
     do {                                                                                                               \
@@ -302,9 +425,15 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
     uint32_t *d_status = static_cast<uint32_t *>(g_ctx.buf[6]);
     const uint8_t *src = static_cast<const uint8_t *>(stream);
     uint8_t *dst = static_cast<uint8_t *>(out);
-    cudaEvent_t *ev_up = g_ctx.ev;          // 8, round robin
-    cudaEvent_t *ev_k0 = g_ctx.ev + 8;      // 2: K0 of a piece finished (its maps are ready)
-    cudaEvent_t *ev_dec = g_ctx.ev + 10;    // 2: decode of a piece finished (its workspace is free)
+    cudaEvent_t *ev_up = g_ctx.ev; // 8, round robin
+    PieceResources r;
+    for (int s = 0; s < 2; ++s) {
+        r.ws[s] = g_ctx.buf[2 + s];
+        r.offs[s] = static_cast<uint64_t *>(g_ctx.buf[4 + s]);
+        r.ev_k0[s] = g_ctx.ev[8 + s];
+        r.ev_dec[s] = g_ctx.ev[10 + s];
+    }
+    r.s_run = g_ctx.s_run, r.s_dec = g_ctx.s_dec, r.h_small = g_ctx.h_small;
 
     CU(cudaMemsetAsync(d_status, 0, 4, g_ctx.s_run), "memset");
     uint64_t issued = 0; // pieces whose upload has been enqueued (at most 8 ahead of the consumer)
@@ -319,69 +448,22 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
     while (issued < n_pieces && issued < 8)
         CU(issue_upload(), "H2D copy");
 
-    uint64_t rs = hdr; // stream offset of the first block that is not decoded yet
-    uint64_t ob = 0;   // blocks decoded so far
-    uint64_t launches = 0, rounds_used = 0;
-    for (uint64_t p = 0; p < n_pieces; ++p) {
-        const bool last = p + 1 == n_pieces;
-        const uint64_t hi = std::min((p + 1) * piece, stream_bytes);
-        CU(cudaStreamWaitEvent(g_ctx.s_run, ev_up[p & 7], 0), "stream wait");
-        if (issued < n_pieces) // keep the upload queue full (the event slot of piece p is free again)
-            CU(issue_upload(), "H2D copy");
-        if (hi <= rs)
-            continue;
-        const uint64_t region = hi - rs;
-        if (region > region_cap) {
-            cudaDeviceSynchronize();
-            return fail_msg(SNAPPY_B200_ERR_FRAMING, "a block of the stream is larger than any 64 KiB block can be");
-        }
-        const int s = (int)(rounds_used & 1);
-        void *ws = g_ctx.buf[2 + s];
-        uint64_t *d_offsets = static_cast<uint64_t *>(g_ctx.buf[4 + s]);
-        if (rounds_used >= 2) // the decode that last read this workspace must be done
-            CU(cudaStreamWaitEvent(g_ctx.s_run, ev_dec[s], 0), "stream wait");
-        const uint64_t blocks_left = nb - ob;
-        const uint64_t out_left = total - ob * kBlock;
-        // K0 on the not-yet-decoded tail; offsets come out relative to d_stream + rs
-        CU(run_index(d_stream + rs, region, 0, last ? out_left : 0, d_offsets, d_status, ws, g_ctx.s_run, &launches,
-                     !last, blocks_left),
-           "index launch");
-        CU(cudaEventRecord(ev_k0[s], g_ctx.s_run), "event record");
-        CU(cudaMemcpyAsync(g_ctx.h_small, index_total(ws, region), 8, cudaMemcpyDeviceToHost, g_ctx.s_run), "read-back");
-        CU(cudaMemcpyAsync(g_ctx.h_small + 1, d_status, 4, cudaMemcpyDeviceToHost, g_ctx.s_run), "read-back");
-        CU(cudaStreamSynchronize(g_ctx.s_run), "index");
-        const uint32_t status = (uint32_t)g_ctx.h_small[1];
-        if (status) {
-            cudaDeviceSynchronize();
-            return status_error(status);
-        }
-        const uint64_t produced = g_ctx.h_small[0];
-        // complete blocks: all of their elements are on the device and the start of the next
-        // block is known (it is an element start inside the region)
-        uint64_t kdone = last ? blocks_left : produced / kBlock;
-        if (!last && kdone > 0 && produced == kdone * kBlock)
-            --kdone; // the start of block kdone may lie just beyond the region: wait for more bytes
-        if (kdone > blocks_left)
-            kdone = blocks_left;
-        if (kdone == 0)
-            continue;
-        ++rounds_used;
-        const uint64_t out_bytes_now = last ? out_left : kdone * kBlock;
-        CU(cudaMemcpyAsync(g_ctx.h_small + 2, d_offsets + kdone, 8, cudaMemcpyDeviceToHost, g_ctx.s_run), "read-back");
-        // decode on its own stream: K0 of the next piece does not wait for it
-        CU(cudaStreamWaitEvent(g_ctx.s_dec, ev_k0[s], 0), "stream wait");
-        CU(launch_decode_seg(d_stream + rs, 0, d_offsets, index_starts(ws, region), kdone, out_bytes_now,
-                             d_out + ob * kBlock, d_status, g_ctx.s_dec, &launches),
-           "decode launch");
-        CU(cudaEventRecord(ev_dec[s], g_ctx.s_dec), "event record");
-        CU(cudaStreamWaitEvent(g_ctx.s_down, ev_dec[s], 0), "stream wait");
-        CU(cudaMemcpyAsync(dst + ob * kBlock, d_out + ob * kBlock, out_bytes_now, cudaMemcpyDeviceToHost, g_ctx.s_down),
-           "D2H copy");
-        CU(cudaStreamSynchronize(g_ctx.s_run), "read-back");
-        rs += g_ctx.h_small[2];
-        ob += kdone;
-    }
-    add_launches(launches);
+    PieceHooks hooks;
+    hooks.before_piece = [&](uint64_t p, cudaStream_t s_run) -> cudaError_t {
+        cudaError_t e = cudaStreamWaitEvent(s_run, ev_up[p & 7], 0);
+        if (e == cudaSuccess && issued < n_pieces) // keep the upload queue full (the event slot is free again)
+            e = issue_upload();
+        return e;
+    };
+    hooks.after_decode = [&](uint64_t first, uint64_t bytes, cudaEvent_t done) -> cudaError_t {
+        cudaError_t e = cudaStreamWaitEvent(g_ctx.s_down, done, 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(dst + first, d_out + first, bytes, cudaMemcpyDeviceToHost, g_ctx.s_down);
+        return e;
+    };
+    const int rc = decode_pieces(d_stream, stream_bytes, hdr, total, d_out, nullptr, d_status, piece, r, hooks);
+    if (rc != SNAPPY_B200_OK)
+        return rc;
     CU(cudaStreamSynchronize(g_ctx.s_dec), "decode");
     CU(cudaMemcpyAsync(g_ctx.h_small + 1, d_status, 4, cudaMemcpyDeviceToHost, g_ctx.s_run), "read-back");
     CU(cudaStreamSynchronize(g_ctx.s_run), "decode");
@@ -389,9 +471,60 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
     const uint32_t status = (uint32_t)g_ctx.h_small[1];
     if (status)
         return status_error(status);
-    if (ob != nb)
-        return fail_msg(SNAPPY_B200_ERR_CORRUPT, "the stream ends before its declared length is reached");
     *out_bytes = total;
+    return SNAPPY_B200_OK;
+}
+
+// ---- device-level index-less decode (include/snappy_b200.h): the same piecewise loop on a
+// device-resident stream, with a library-owned second stream for the decode kernels.
+// A device-resident stream is decoded as ONE piece: K0 has about 2 ms of latency-bound fixed cost
+// per call (measured, profiles/), so splitting only pays when there is a transfer to hide.
+size_t snappy_b200_decompress_workspace_bytes(uint64_t stream_bytes, uint64_t total_out)
+{
+    const uint64_t piece = std::max<uint64_t>(stream_bytes, 1);
+    const uint64_t nb = (total_out + kBlock - 1) / kBlock;
+    const size_t per_slot = align_up(index_workspace_bytes(piece_region_cap(stream_bytes, piece)), 256) +
+                            align_up((nb + 2) * 8, 256);
+    return 2 * per_slot + 256;
+}
+
+int snappy_b200_decompress_device(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
+                                  uint64_t total_out, uint8_t *d_out, uint64_t *d_block_offsets, uint32_t *d_status,
+                                  void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (!d_stream || !d_status || !d_workspace || (!d_out && total_out))
+        return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    if (body_offset > stream_bytes || stream_bytes >= (1ull << 40))
+        return fail_msg(SNAPPY_B200_ERR_ARG, "bad stream size / body offset");
+    if (workspace_bytes < snappy_b200_decompress_workspace_bytes(stream_bytes, total_out))
+        return fail_msg(SNAPPY_B200_ERR_ARG, "workspace too small (see snappy_b200_decompress_workspace_bytes)");
+    if (total_out == 0)
+        return SNAPPY_B200_OK;
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    CU(g_ctx.init(), "context init");
+    const uint64_t piece = std::max<uint64_t>(stream_bytes, 1);
+    const uint64_t nb = (total_out + kBlock - 1) / kBlock;
+    const size_t ws_slot = align_up(index_workspace_bytes(piece_region_cap(stream_bytes, piece)), 256);
+    const size_t off_slot = align_up((nb + 2) * 8, 256);
+    uint8_t *w = static_cast<uint8_t *>(d_workspace);
+    PieceResources r;
+    for (int s = 0; s < 2; ++s) {
+        r.ws[s] = w + s * (ws_slot + off_slot);
+        r.offs[s] = reinterpret_cast<uint64_t *>(w + s * (ws_slot + off_slot) + ws_slot);
+        r.ev_k0[s] = g_ctx.ev[16 + s];
+        r.ev_dec[s] = g_ctx.ev[18 + s];
+    }
+    r.s_run = static_cast<cudaStream_t>(stream);
+    r.s_dec = g_ctx.s_dec;
+    r.h_small = g_ctx.h_small + 8;
+    PieceHooks hooks; // nothing to wait for, nothing to download
+    const int rc = decode_pieces(d_stream, stream_bytes, body_offset, total_out, d_out, d_block_offsets, d_status,
+                                 piece, r, hooks);
+    if (rc != SNAPPY_B200_OK)
+        return rc;
+    // join: work the caller enqueues next on `stream` sees the decoded output
+    CU(cudaEventRecord(g_ctx.ev[20], g_ctx.s_dec), "event record");
+    CU(cudaStreamWaitEvent(r.s_run, g_ctx.ev[20], 0), "stream wait");
     return SNAPPY_B200_OK;
 }
 
