@@ -32,7 +32,7 @@
 //                      corrected instead of one per round.  An adversarial stream degrades to
 //                      sequential but stays correct.  k_group_final then chases every live group
 //                      once more from its true entry and records the entry of each segment.
-//   C  k_index_outlen  every live segment sums the output bytes of its elements and stores the
+//   C  (k_group_final) every live segment sums the output bytes of its elements and stores the
 //                      exact bit map of its element starts (for the segment-driven decoder)
 //      k_scan_*        exclusive scan -> output offset of every segment
 //   D  k_index_blocks  every live segment walks once more and records the stream offset of
@@ -57,10 +57,13 @@ struct Elem {
 
 // Decodes the element header at body offset e (reference: decompressor :290-333, do_literal
 // :193-224).  Bytes past the end of the body read as zero and clear `ok`.
+// LDG: read through the read-only global path; otherwise plain loads (body may then be a view of
+// a shared-memory copy: body + e must be a valid address for every e that is touched).
+template <bool LDG = true>
 __device__ __forceinline__ Elem decode_at(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t e)
 {
     Elem r;
-    const uint32_t tag = __ldg(body + e);
+    const uint32_t tag = LDG ? __ldg(body + e) : body[e];
     const uint32_t type = tag & 3u;
     uint32_t extra; // header bytes after the tag
     if (type == 0) {
@@ -73,7 +76,7 @@ __device__ __forceinline__ Elem decode_at(const uint8_t *__restrict__ body, uint
     uint32_t raw = 0;
     if (type == 0 && extra && r.ok) {
         for (uint32_t k = 0; k < extra; ++k)
-            raw |= (uint32_t)__ldg(body + e + 1 + k) << (8 * k);
+            raw |= (uint32_t)(LDG ? __ldg(body + e + 1 + k) : body[e + 1 + k]) << (8 * k);
     }
     if (type == 0) {
         const uint64_t len = (uint64_t)((tag >> 2) >= 60 ? raw : (tag >> 2)) + 1;
@@ -109,6 +112,7 @@ struct Path {
 
 // Walks from e until the segment [seg_lo, seg_hi) is left, or (when `old` is given) until an
 // offset already on the old path is met.  Visited offsets are recorded in `fresh`.
+template <bool LDG = true>
 __device__ __forceinline__ uint64_t walk(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t seg_lo,
                                          uint64_t seg_hi, uint64_t e, const Path *old, Path &fresh, bool &merged)
 {
@@ -120,7 +124,7 @@ __device__ __forceinline__ uint64_t walk(const uint8_t *__restrict__ body, uint6
             return e;
         }
         fresh.set(rel);
-        const Elem el = decode_at(body, body_len, e);
+        const Elem el = decode_at<LDG>(body, body_len, e);
         e += el.size; // seg_hi <= body_len, sizes < 2^33: no overflow
     }
     return e;
@@ -186,8 +190,13 @@ struct GroupStage {
     uint8_t entry[kGroup];
 };
 
-__device__ __forceinline__ void group_stage(GroupStage &sm, uint64_t g, uint64_t nseg,
-                                            const uint4 *__restrict__ paths, const uint64_t *__restrict__ exits)
+// Stages the per-segment records of group g.  (Staging the group's 8 KiB of stream bytes as
+// well, so that the fallback walks of mis-speculated chains read shared memory, was measured
+// and lost: it re-reads the whole stream in every pass for the benefit of the garbage regions.)
+__device__ __forceinline__ const uint8_t *group_stage(GroupStage &sm, uint64_t g, uint64_t nseg,
+                                                      const uint8_t *__restrict__ body, uint64_t body_len,
+                                                      const uint4 *__restrict__ paths,
+                                                      const uint64_t *__restrict__ exits)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t s0 = g * kGroup;
@@ -197,15 +206,16 @@ __device__ __forceinline__ void group_stage(GroupStage &sm, uint64_t g, uint64_t
         sm.paths[k] = ok ? paths[s0 + k] : make_uint4(0, 0, 0, 0);
         sm.exits[k] = ok ? exits[s0 + k] : 0;
     }
+    (void)body_len;
     __syncwarp();
+    return body;
 }
 
-// Chases the element chain from body offset e to the end of group g (warp-uniform).  vis gets
-// one bit per segment that the chain entered on that segment's recorded path (from such a
-// point on the chain is the recorded one).  When record is set, the entry of every segment is
-// left in sm.entry (kDead for segments the chain jumps over).
-__device__ __forceinline__ uint64_t group_chase(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
-                                                GroupStage &sm, uint64_t g, uint64_t e, uint64_t &vis, bool record)
+// Chases the element chain from body offset e to the end of group g (warp-uniform).  vis gets one bit per segment that the chain entered on that
+// segment's recorded path (from such a point on the chain is the recorded one).  When record is
+// set, the entry of every segment is left in sm.entry (kDead for segments the chain jumps over).
+__device__ __forceinline__ uint64_t group_chase(const uint8_t *vbody, uint64_t body_len, uint64_t nseg, GroupStage &sm,
+                                                uint64_t g, uint64_t e, uint64_t &vis, bool record)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t s0 = g * kGroup;
@@ -234,7 +244,7 @@ __device__ __forceinline__ uint64_t group_chase(const uint8_t *__restrict__ body
             fresh.clear();
             bool merged;
             const uint64_t lo = sg * kSeg, hi = min(lo + kSeg, body_len);
-            const uint64_t x = walk(body, body_len, lo, hi, e, &p, fresh, merged);
+            const uint64_t x = walk<true>(vbody, body_len, lo, hi, e, &p, fresh, merged);
             if (merged) {
                 vis |= 1ull << k;
                 e = sm.exits[k];
@@ -261,9 +271,9 @@ __global__ void __launch_bounds__(kGroupCta) k_group_init(const uint8_t *__restr
     if (g >= ngroup)
         return;
     GroupStage &sm = stage[threadIdx.x >> 5];
-    group_stage(sm, g, nseg, paths, exits);
+    const uint8_t *vbody = group_stage(sm, g, nseg, body, body_len, paths, exits);
     uint64_t vis;
-    const uint64_t x = group_chase(body, body_len, nseg, sm, g, g * kGroupBytes, vis, false);
+    const uint64_t x = group_chase(vbody, body_len, nseg, sm, g, g * kGroupBytes, vis, false);
     if ((threadIdx.x & 31) == 0) {
         g_exit[g] = x;
         g_vis[g] = vis;
@@ -302,7 +312,7 @@ __global__ void __launch_bounds__(128) k_group_scatter(const uint8_t *__restrict
         // Groups jumped over hold no element start (only a live source may say so: a dead
         // group's chase is pure speculation).  An element of this framing never spans more than
         // one 64 KiB block (+ header), which bounds the work a mis-speculated literal can cause;
-        // a true element that long is reported as SNAPPY_B200_ST_FRAMING by k_index_outlen.
+        // a true element that long is reported as SNAPPY_B200_ST_FRAMING by k_group_final.
         const uint64_t vmax = min(min(u, ngroup), g + 2 + (kBlock + 1024) / kGroupBytes);
         for (uint64_t v = g + 1; v < vmax; ++v)
             atomicMin(g_claim + v, (unsigned long long)((g << 24) | kGMark));
@@ -383,21 +393,25 @@ __global__ void __launch_bounds__(kGroupCta) k_group_apply(const uint8_t *__rest
     if (((g_vis[g] >> (sg - g * kGroup)) & 1ull) && p.test((uint32_t)(e - sg * kSeg)))
         return; // same exit, and everything the old chain recorded still holds from here on
     GroupStage &sm = stage[threadIdx.x >> 5];
-    group_stage(sm, g, nseg, paths, exits);
+    const uint8_t *vbody = group_stage(sm, g, nseg, body, body_len, paths, exits);
     uint64_t vis;
-    const uint64_t x = group_chase(body, body_len, nseg, sm, g, e, vis, false);
+    const uint64_t x = group_chase(vbody, body_len, nseg, sm, g, e, vis, false);
     if (lane == 0) {
         g_exit[g] = x;
         g_vis[g] = vis;
     }
 }
 
+// Last pass over the tags.  Every live group chases once more from its true entry, which gives
+// the entry of each of its segments; every live segment is then walked from that entry (C): the
+// output bytes of the elements that start in it are summed, and the (speculative) path map is
+// replaced by the exact map of element starts -- what the segment-driven decoder consumes.
 __global__ void __launch_bounds__(kGroupCta) k_group_final(const uint8_t *__restrict__ body, uint64_t body_len,
-                                                           uint64_t nseg, uint64_t ngroup,
-                                                           const uint4 *__restrict__ paths,
+                                                           uint64_t nseg, uint64_t ngroup, uint4 *__restrict__ paths,
                                                            const uint64_t *__restrict__ exits,
                                                            const uint32_t *__restrict__ g_entry,
-                                                           uint8_t *__restrict__ entry)
+                                                           uint64_t *__restrict__ outlen,
+                                                           uint32_t *__restrict__ status, int open_end)
 {
     __shared__ GroupStage stage[kGroupCta / 32];
     const uint64_t g = blockIdx.x * (uint64_t)(kGroupCta / 32) + (threadIdx.x >> 5);
@@ -406,58 +420,48 @@ __global__ void __launch_bounds__(kGroupCta) k_group_final(const uint8_t *__rest
     const uint32_t lane = threadIdx.x & 31;
     GroupStage &sm = stage[threadIdx.x >> 5];
     const uint32_t ge = g_entry[g];
-    if (ge & kGDead) {
-        sm.entry[lane] = (uint8_t)kDead;
-        sm.entry[lane + 32] = (uint8_t)kDead;
-        __syncwarp();
-    } else {
-        group_stage(sm, g, nseg, paths, exits);
-        uint64_t vis;
-        (void)group_chase(body, body_len, nseg, sm, g, g * kGroupBytes + ge, vis, true);
-    }
     const uint64_t s0 = g * kGroup;
-    if (s0 + lane < nseg)
-        entry[s0 + lane] = sm.entry[lane];
-    if (s0 + lane + 32 < nseg)
-        entry[s0 + lane + 32] = sm.entry[lane + 32];
-}
-
-// C: output bytes produced by the elements that start in each live segment.  The walk visits
-// exactly the true element starts of the segment, so it also replaces the (speculative) path
-// map by the exact map of element starts -- what the segment-driven decoder consumes.
-__global__ void __launch_bounds__(256) k_index_outlen(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
-                                                      const uint8_t *__restrict__ entry, uint64_t *__restrict__ outlen,
-                                                      uint4 *__restrict__ starts, uint32_t *__restrict__ status,
-                                                      int open_end)
-{
-    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (t >= nseg)
-        return;
-    uint64_t sum = 0;
-    Path p;
-    p.clear();
-    const uint32_t en = entry[t];
-    if (!(en & kDead)) {
-        const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
-        uint64_t e = lo + en;
-        while (e < hi) {
-            const Elem el = decode_at(body, body_len, e);
-            if (!el.ok || e + el.size > body_len) {
-                // the element runs past the bytes we have: an error for a whole stream, the
-                // normal end of a partial one (open_end: the rest has not been uploaded yet)
-                if (!open_end)
-                    atomicOr(status, SNAPPY_B200_ST_CORRUPT);
-                break;
+    if (ge & kGDead) {
+        for (uint32_t k = lane; k < kGroup; k += 32)
+            if (s0 + k < nseg) {
+                outlen[s0 + k] = 0;
+                paths[s0 + k] = make_uint4(0, 0, 0, 0);
             }
-            if (el.out > kBlock)
-                atomicOr(status, SNAPPY_B200_ST_FRAMING);
-            p.set((uint32_t)(e - lo));
-            sum += el.out;
-            e += el.size;
-        }
+        return;
     }
-    outlen[t] = sum;
-    starts[t] = make_uint4(p.bits[0], p.bits[1], p.bits[2], p.bits[3]);
+    const uint8_t *vbody = group_stage(sm, g, nseg, body, body_len, paths, exits);
+    uint64_t vis;
+    (void)group_chase(vbody, body_len, nseg, sm, g, g * kGroupBytes + ge, vis, true);
+    for (uint32_t k = lane; k < kGroup; k += 32) {
+        const uint64_t t = s0 + k;
+        if (t >= nseg)
+            break;
+        uint64_t sum = 0;
+        Path p;
+        p.clear();
+        const uint32_t en = sm.entry[k];
+        if (!(en & kDead)) {
+            const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
+            uint64_t e = lo + en;
+            while (e < hi) {
+                const Elem el = decode_at<true>(vbody, body_len, e);
+                if (!el.ok || e + el.size > body_len) {
+                    // the element runs past the bytes we have: an error for a whole stream, the
+                    // normal end of a partial one (open_end: the rest has not been uploaded yet)
+                    if (!open_end)
+                        atomicOr(status, SNAPPY_B200_ST_CORRUPT);
+                    break;
+                }
+                if (el.out > kBlock)
+                    atomicOr(status, SNAPPY_B200_ST_FRAMING);
+                p.set((uint32_t)(e - lo));
+                sum += el.out;
+                e += el.size;
+            }
+        }
+        outlen[t] = sum;
+        paths[t] = make_uint4(p.bits[0], p.bits[1], p.bits[2], p.bits[3]);
+    }
 }
 
 // Exclusive scan of a u64 array (one entry per 128 stream bytes, so millions of entries): tile
@@ -565,36 +569,72 @@ __global__ void __launch_bounds__(kScanCta) k_scan_apply(const uint64_t *__restr
     }
 }
 
-// D: stream offset of the element that opens each 64 KiB output block.
+// D: stream offset of the element that opens each 64 KiB output block: one thread per block.  The
+// segment is found by binary search over the output offsets (the last segment whose first
+// element starts at or before the block boundary), the element by walking that segment's
+// starts.  A boundary that falls inside an element (legal raw Snappy, never produced by this
+// framing) is reported as SNAPPY_B200_ST_FRAMING.
 __global__ void __launch_bounds__(256) k_index_blocks(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
-                                                      const uint8_t *__restrict__ entry,
-                                                      const uint64_t *__restrict__ outoff, uint64_t body_offset,
+                                                      const uint4 *__restrict__ starts,
+                                                      const uint64_t *__restrict__ outoff,
+                                                      const uint64_t *__restrict__ total, uint64_t body_offset,
                                                       uint64_t n_blocks, uint64_t *__restrict__ block_offsets,
-                                                      uint32_t *__restrict__ status)
+                                                      uint32_t *__restrict__ status, int open_end)
 {
-    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (t >= nseg)
+    const uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (b >= n_blocks)
         return;
-    const uint32_t en = entry[t];
-    if (en & kDead)
-        return;
-    const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
-    uint64_t e = lo + en, op = outoff[t];
-    while (e < hi) {
-        const Elem el = decode_at(body, body_len, e);
-        const uint64_t within = op & (kBlock - 1);
-        if (within == 0) { // e is a true element start even if the element itself is cut off
-            const uint64_t bi = op / kBlock;
-            if (bi < n_blocks)
-                block_offsets[bi] = body_offset + e;
-        }
-        if (!el.ok || e + el.size > body_len)
-            break; // already flagged by k_index_outlen (or the open end of a partial stream)
-        if (within + el.out > kBlock)
-            atomicOr(status, SNAPPY_B200_ST_FRAMING);
-        op += el.out;
-        e += el.size;
+    const uint64_t target = b * (uint64_t)kBlock;
+    if (target > *total || (target == *total && !open_end))
+        return; // beyond what the stream produces (k_index_finish reports a wrong total)
+    // last segment t with outoff[t] <= target
+    uint64_t lo = 0, hi = nseg; // invariant: outoff[lo] <= target (outoff[0] == 0), answer in [lo, hi)
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if (outoff[mid] <= target)
+            lo = mid;
+        else
+            hi = mid;
     }
+    const uint64_t t = lo;
+    const uint4 sv = starts[t];
+    const uint32_t R[4] = {sv.x, sv.y, sv.z, sv.w};
+    uint64_t op = outoff[t];
+    const uint64_t seg_lo = t * kSeg;
+    bool found = false;
+    for (uint32_t w = 0; w < 4 && !found && op <= target; ++w) {
+        uint32_t bits = R[w];
+        while (bits) {
+            const uint32_t bit = (uint32_t)__ffs((int)bits) - 1;
+            bits &= bits - 1;
+            const uint64_t e = seg_lo + 32 * w + bit;
+            if (op == target) {
+                block_offsets[b] = body_offset + e;
+                found = true;
+                break;
+            }
+            if (op > target)
+                break;
+            op += decode_at(body, body_len, e).out;
+        }
+    }
+    if (found)
+        return;
+    if (op == target && open_end) {
+        // open-ended region: the element that opens the block is the one cut off by the end of
+        // the bytes we have.  The chain reaches its start (right after the last complete element
+        // of the segment), but an incomplete element has no bit in the map.
+        for (int w = 3; w >= 0; --w)
+            if (R[w]) {
+                const uint64_t e = seg_lo + 32 * w + (31 - __clz((int)R[w]));
+                const uint64_t e_end = e + decode_at(body, body_len, e).size;
+                if (e_end < body_len)
+                    block_offsets[b] = body_offset + e_end;
+                break;
+            }
+        return; // (if it is not known yet the host pipeline does not use this entry)
+    }
+    atomicOr(status, SNAPPY_B200_ST_FRAMING);
 }
 
 __global__ void k_index_finish(const uint64_t *__restrict__ total, uint64_t total_out, uint64_t stream_bytes,
@@ -663,7 +703,7 @@ static IndexWorkspace carve(void *ws, uint64_t stream_bytes)
     return w;
 }
 
-// The exact element-start maps k_index_outlen leaves behind (one uint4 per 128-byte segment).
+// The exact element-start maps k_group_final leaves behind (one uint4 per 128-byte segment).
 const uint4 *index_starts(void *d_ws, uint64_t stream_bytes) { return carve(d_ws, stream_bytes).paths; }
 
 static uint64_t g_last_rounds = 0;
@@ -732,15 +772,16 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
             break;
         }
     }
-    k_group_final<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.entry);
-    *launches += 1;
-    k_index_outlen<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outlen, w.paths, d_status, open_end);
+    k_group_final<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.outlen,
+                                               d_status, open_end);
     const uint64_t ntile = (nseg + kScanTile - 1) / kScanTile;
     k_scan_tile_sums<<<(unsigned)ntile, kScanCta, 0, st>>>(w.outlen, nseg, w.tile_sums);
     k_scan_tiles<<<1, kScanCta, 0, st>>>(w.tile_sums, ntile, w.total);
     k_scan_apply<<<(unsigned)ntile, kScanCta, 0, st>>>(w.outlen, nseg, w.tile_sums, w.outoff);
-    k_index_blocks<<<grid, 256, 0, st>>>(body, body_len, nseg, w.entry, w.outoff, body_offset, n_blocks,
-                                         d_block_offsets, d_status);
+    if (n_blocks)
+        k_index_blocks<<<(unsigned)((n_blocks + 255) / 256), 256, 0, st>>>(body, body_len, nseg, w.paths, w.outoff,
+                                                                          w.total, body_offset, n_blocks,
+                                                                          d_block_offsets, d_status, open_end);
     k_index_finish<<<1, 32, 0, st>>>(w.total, total_out, stream_bytes, n_blocks, d_block_offsets, d_status, open_end);
     *launches += 6;
     return cudaGetLastError();
