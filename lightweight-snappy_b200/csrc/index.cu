@@ -187,16 +187,13 @@ constexpr int kGroupCta = 128;                 // 4 warps = 4 groups per CTA
 struct GroupStage {
     uint4 paths[kGroup];
     uint64_t exits[kGroup];
+    uint32_t claim[kGroup];
     uint8_t entry[kGroup];
 };
 
-// Stages the per-segment records of group g.  (Staging the group's 8 KiB of stream bytes as
-// well, so that the fallback walks of mis-speculated chains read shared memory, was measured
-// and lost: it re-reads the whole stream in every pass for the benefit of the garbage regions.)
-__device__ __forceinline__ const uint8_t *group_stage(GroupStage &sm, uint64_t g, uint64_t nseg,
-                                                      const uint8_t *__restrict__ body, uint64_t body_len,
-                                                      const uint4 *__restrict__ paths,
-                                                      const uint64_t *__restrict__ exits)
+// Stages the per-segment records of group g.
+__device__ __forceinline__ void group_stage(GroupStage &sm, uint64_t g, uint64_t nseg, const uint4 *__restrict__ paths,
+                                            const uint64_t *__restrict__ exits)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t s0 = g * kGroup;
@@ -206,62 +203,137 @@ __device__ __forceinline__ const uint8_t *group_stage(GroupStage &sm, uint64_t g
         sm.paths[k] = ok ? paths[s0 + k] : make_uint4(0, 0, 0, 0);
         sm.exits[k] = ok ? exits[s0 + k] : 0;
     }
-    (void)body_len;
     __syncwarp();
-    return body;
 }
 
-// Chases the element chain from body offset e to the end of group g (warp-uniform).  vis gets one bit per segment that the chain entered on that
-// segment's recorded path (from such a point on the chain is the recorded one).  When record is
-// set, the entry of every segment is left in sm.entry (kDead for segments the chain jumps over).
-__device__ __forceinline__ uint64_t group_chase(const uint8_t *vbody, uint64_t body_len, uint64_t nseg, GroupStage &sm,
-                                                uint64_t g, uint64_t e, uint64_t &vis, bool record)
+// Writes the (possibly improved) per-segment records back, so that later passes find the chain
+// on the recorded paths.
+__device__ __forceinline__ void group_unstage(const GroupStage &sm, uint64_t g, uint64_t nseg, uint4 *__restrict__ paths,
+                                              uint64_t *__restrict__ exits)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t s0 = g * kGroup;
-    const uint64_t s1 = min(s0 + kGroup, nseg);
-    const uint64_t g_hi = min(s1 * kSeg, body_len);
-    vis = 0;
-    if (record) {
-        sm.entry[lane] = (uint8_t)kDead;
-        sm.entry[lane + 32] = (uint8_t)kDead;
-        __syncwarp();
-    }
-    while (e < g_hi) {
-        const uint64_t sg = e / kSeg;
-        const uint32_t k = (uint32_t)(sg - s0);
-        const uint32_t rel = (uint32_t)(e - sg * kSeg);
-        if (record && lane == 0)
-            sm.entry[k] = (uint8_t)rel;
-        const uint4 pv = sm.paths[k];
-        Path p;
-        p.bits[0] = pv.x, p.bits[1] = pv.y, p.bits[2] = pv.z, p.bits[3] = pv.w;
-        if (p.test(rel)) {
-            vis |= 1ull << k;
-            e = sm.exits[k];
-        } else {
-            Path fresh;
-            fresh.clear();
-            bool merged;
-            const uint64_t lo = sg * kSeg, hi = min(lo + kSeg, body_len);
-            const uint64_t x = walk<true>(vbody, body_len, lo, hi, e, &p, fresh, merged);
-            if (merged) {
-                vis |= 1ull << k;
-                e = sm.exits[k];
-            } else {
-                e = x;
-            }
+#pragma unroll
+    for (uint32_t k = lane; k < kGroup; k += 32)
+        if (s0 + k < nseg) {
+            paths[s0 + k] = sm.paths[k];
+            exits[s0 + k] = sm.exits[k];
         }
+}
+
+// Makes `rel` the entry of staged segment k (global index t): if it is not on the recorded path
+// the tags are walked from it until the path is met (the exit stands, the path grows) or the
+// segment is left (a different chain: path and exit are replaced).
+__device__ __forceinline__ void segment_enter(const uint8_t *__restrict__ body, uint64_t body_len, GroupStage &sm,
+                                              uint32_t k, uint64_t t, uint32_t rel)
+{
+    const uint4 pv = sm.paths[k];
+    Path p;
+    p.bits[0] = pv.x, p.bits[1] = pv.y, p.bits[2] = pv.z, p.bits[3] = pv.w;
+    if (p.test(rel))
+        return;
+    Path fresh;
+    fresh.clear();
+    bool merged;
+    const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
+    const uint64_t x = walk(body, body_len, lo, hi, lo + rel, &p, fresh, merged);
+    if (merged) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+            fresh.bits[w] |= p.bits[w];
+    } else {
+        sm.exits[k] = x;
+    }
+    sm.paths[k] = make_uint4(fresh.bits[0], fresh.bits[1], fresh.bits[2], fresh.bits[3]);
+}
+
+// Resolves the element chain of group g from body offset e0 (which lies in the group) to the
+// end of the group: the same relaxation as between groups, but over the 64 staged segments and
+// inside one warp -- lane l owns segments l and l+32, so the tag walks of different segments run
+// in parallel instead of one after the other.  Every segment publishes the exit of its current
+// walk to the segment it lands in and (if live) marks the segments a long element jumps over
+// as dead; dead segments keep publishing at low priority; the lowest source wins.  The segment
+// that holds e0 is known, so the correct prefix grows every round and the fixed point is the
+// chain.  Leaves the entry of every segment in sm.entry (kDead where no element starts), sets
+// vis to the live segments and returns the offset at which the chain leaves the group.
+__device__ __forceinline__ uint64_t group_resolve(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
+                                                  GroupStage &sm, uint64_t g, uint64_t e0, uint64_t &vis)
+{
+    constexpr uint32_t kNoClaim = 0xffffffffu, kLow = 0x80000000u;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t s0 = g * kGroup;
+    const uint32_t nk = (uint32_t)(min(s0 + kGroup, nseg) - s0); // segments in this group
+    const uint64_t g_hi = min((s0 + nk) * kSeg, body_len);
+    const uint32_t k0 = (uint32_t)(e0 / kSeg - s0);
+    const uint32_t rel0 = (uint32_t)(e0 - (s0 + k0) * kSeg);
+    // initial beliefs: the segment of e0 is known, later ones start out at the first offset of
+    // their recorded path (any offset on it leads to the recorded exit), earlier ones hold nothing
+    for (uint32_t k = lane; k < kGroup; k += 32) {
+        const uint4 pv = sm.paths[k];
+        const uint32_t first = pv.x   ? __ffs((int)pv.x) - 1
+                               : pv.y ? 32 + __ffs((int)pv.y) - 1
+                               : pv.z ? 64 + __ffs((int)pv.z) - 1
+                               : pv.w ? 96 + __ffs((int)pv.w) - 1
+                                      : 0;
+        sm.entry[k] = (uint8_t)(k < k0 || k >= nk ? kDead : (k == k0 ? rel0 : first));
+        if (k == k0 && k < nk)
+            segment_enter(body, body_len, sm, k, s0 + k, rel0);
     }
     __syncwarp();
-    return e;
+    for (uint32_t round = 0; round < kGroup + 2; ++round) {
+        for (uint32_t k = lane; k < kGroup; k += 32)
+            sm.claim[k] = kNoClaim;
+        __syncwarp();
+        for (uint32_t k = lane; k < nk; k += 32) {
+            if (k < k0)
+                continue;
+            const bool dead = sm.entry[k] & kDead;
+            const uint64_t x = sm.exits[k];
+            const uint64_t u64 = x / kSeg - s0; // staged index of the landing segment (>= k + 1)
+            const uint32_t u = u64 < kGroup ? (uint32_t)u64 : kGroup;
+            if (!dead) {
+                for (uint32_t v = k + 1; v < min(u, nk); ++v)
+                    atomicMin(&sm.claim[v], (k << 8) | kMark);
+                if (u < nk && x >= body_len)
+                    atomicMin(&sm.claim[u], (k << 8) | kMark);
+            }
+            if (u < nk && x < body_len)
+                atomicMin(&sm.claim[u], (dead ? kLow : 0u) | (k << 8) | (uint32_t)(x - (s0 + u) * kSeg));
+        }
+        __syncwarp();
+        bool changed = false;
+        for (uint32_t k = lane; k < nk; k += 32) {
+            if (k <= k0)
+                continue;
+            const uint32_t c = sm.claim[k];
+            const uint32_t old = sm.entry[k];
+            const uint32_t payload = c & 0xffu;
+            const uint32_t ne = (c == kNoClaim || payload == kMark) ? ((old & 0x7fu) | kDead) : payload;
+            if (ne == old)
+                continue;
+            changed = true;
+            sm.entry[k] = (uint8_t)ne;
+            if (!(ne & kDead))
+                segment_enter(body, body_len, sm, k, s0 + k, ne); // (returns at once if ne is on the path)
+        }
+        __syncwarp();
+        if (!__any_sync(kFull, changed))
+            break;
+    }
+    // live segments, and the exit of the last one
+    const bool live0 = lane < nk && !(sm.entry[lane] & kDead);
+    const bool live1 = lane + 32 < nk && !(sm.entry[lane + 32] & kDead);
+    const unsigned m0 = __ballot_sync(kFull, live0), m1 = __ballot_sync(kFull, live1);
+    vis = (uint64_t)m0 | ((uint64_t)m1 << 32);
+    const uint32_t last = m1 ? 32 + (31 - __clz((int)m1)) : (m0 ? 31 - __clz((int)m0) : k0);
+    (void)g_hi;
+    return sm.exits[last];
 }
 
 // Initial state: every group believes an element starts at its first byte.
 __global__ void __launch_bounds__(kGroupCta) k_group_init(const uint8_t *__restrict__ body, uint64_t body_len,
-                                                          uint64_t nseg, uint64_t ngroup,
-                                                          const uint4 *__restrict__ paths,
-                                                          const uint64_t *__restrict__ exits,
+                                                          uint64_t nseg, uint64_t ngroup, uint4 *__restrict__ paths,
+                                                          uint64_t *__restrict__ exits,
                                                           uint32_t *__restrict__ g_entry, uint64_t *__restrict__ g_exit,
                                                           uint64_t *__restrict__ g_vis,
                                                           unsigned long long *__restrict__ g_claim)
@@ -271,9 +343,10 @@ __global__ void __launch_bounds__(kGroupCta) k_group_init(const uint8_t *__restr
     if (g >= ngroup)
         return;
     GroupStage &sm = stage[threadIdx.x >> 5];
-    const uint8_t *vbody = group_stage(sm, g, nseg, body, body_len, paths, exits);
+    group_stage(sm, g, nseg, paths, exits);
     uint64_t vis;
-    const uint64_t x = group_chase(vbody, body_len, nseg, sm, g, g * kGroupBytes, vis, false);
+    const uint64_t x = group_resolve(body, body_len, nseg, sm, g, g * kGroupBytes, vis);
+    group_unstage(sm, g, nseg, paths, exits);
     if ((threadIdx.x & 31) == 0) {
         g_exit[g] = x;
         g_vis[g] = vis;
@@ -349,9 +422,8 @@ __global__ void __launch_bounds__(128) k_group_scatter(const uint8_t *__restrict
 }
 
 __global__ void __launch_bounds__(kGroupCta) k_group_apply(const uint8_t *__restrict__ body, uint64_t body_len,
-                                                           uint64_t nseg, uint64_t ngroup,
-                                                           const uint4 *__restrict__ paths,
-                                                           const uint64_t *__restrict__ exits,
+                                                           uint64_t nseg, uint64_t ngroup, uint4 *__restrict__ paths,
+                                                           uint64_t *__restrict__ exits,
                                                            uint32_t *__restrict__ g_entry,
                                                            uint64_t *__restrict__ g_exit, uint64_t *__restrict__ g_vis,
                                                            unsigned long long *__restrict__ g_claim,
@@ -393,9 +465,10 @@ __global__ void __launch_bounds__(kGroupCta) k_group_apply(const uint8_t *__rest
     if (((g_vis[g] >> (sg - g * kGroup)) & 1ull) && p.test((uint32_t)(e - sg * kSeg)))
         return; // same exit, and everything the old chain recorded still holds from here on
     GroupStage &sm = stage[threadIdx.x >> 5];
-    const uint8_t *vbody = group_stage(sm, g, nseg, body, body_len, paths, exits);
+    group_stage(sm, g, nseg, paths, exits);
     uint64_t vis;
-    const uint64_t x = group_chase(vbody, body_len, nseg, sm, g, e, vis, false);
+    const uint64_t x = group_resolve(body, body_len, nseg, sm, g, e, vis);
+    group_unstage(sm, g, nseg, paths, exits);
     if (lane == 0) {
         g_exit[g] = x;
         g_vis[g] = vis;
@@ -429,9 +502,10 @@ __global__ void __launch_bounds__(kGroupCta) k_group_final(const uint8_t *__rest
             }
         return;
     }
-    const uint8_t *vbody = group_stage(sm, g, nseg, body, body_len, paths, exits);
+    group_stage(sm, g, nseg, paths, exits);
     uint64_t vis;
-    (void)group_chase(vbody, body_len, nseg, sm, g, g * kGroupBytes + ge, vis, true);
+    (void)group_resolve(body, body_len, nseg, sm, g, g * kGroupBytes + ge, vis);
+    const uint8_t *vbody = body;
     for (uint32_t k = lane; k < kGroup; k += 32) {
         const uint64_t t = s0 + k;
         if (t >= nseg)
