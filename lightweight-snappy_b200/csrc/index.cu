@@ -11,27 +11,28 @@
 //                      and the offset at which it leaves the segment.  Snappy streams
 //                      re-synchronise within a few elements, so most of these walks merge
 //                      into the true element chain long before the segment ends.
-//   A' k_index_link    the exit of segment t-1 is walked into segment t until it meets t's path,
-//                      and those offsets are added to the path
-//   B  k_group_*       the segments are taken 64 at a time (8 KiB "groups"), one thread per
-//                      group.  A group's walk is a chase through its segments: where the chain
-//                      enters a segment on that segment's recorded path the segment's exit is
-//                      taken as is, otherwise the tags are walked until the path is met.  Groups
-//                      are then resolved by relaxation rounds (k_group_scatter / k_group_apply):
-//                      every group publishes the exit of its current chase to the group it lands
-//                      in, and a live group marks the groups a long literal jumps over as "dead"
-//                      (holding no element start).  A group that was itself marked dead keeps
-//                      publishing its exit, but at low priority; among equal priorities the
-//                      lowest source wins.  A group whose entry changed re-chases from the new
-//                      entry unless that entry lies on its old chain.  Group 0's entry is known,
-//                      every other group is claimed or marked by a live predecessor, so the
-//                      beliefs are correct on a prefix that grows every round, and a round that
-//                      changes nothing is the unique fixed point = the true chain.  Keeping dead
-//                      groups talking matters: when a mis-speculated "long literal" wrongly
-//                      kills a run of groups they all come back in the round after it is
-//                      corrected instead of one per round.  An adversarial stream degrades to
-//                      sequential but stays correct.  k_group_final then chases every live group
-//                      once more from its true entry and records the entry of each segment.
+//   B  k_group_*       the segments are taken 64 at a time (8 KiB "groups"), one warp per group.
+//                      Inside a group the chain is resolved by a relaxation over its 64 segments
+//                      (group_resolve): every segment publishes the exit of its current walk to
+//                      the segment it lands in, a live segment marks the segments a long
+//                      element jumps over as "dead" (holding no element start), a segment that
+//                      was itself marked dead keeps publishing its exit at low priority, the
+//                      lowest source wins, and a segment whose entry changed re-walks from the
+//                      new entry until it meets its recorded path.  The entry of one segment is
+//                      known, every other segment is claimed or marked by a live predecessor, so
+//                      the beliefs are correct on a prefix that grows every round, and a round
+//                      that changes nothing is the unique fixed point = the chain.  (ASCII text
+//                      makes mis-speculated walks take ~27-byte strides, so about half of the
+//                      128-byte walks do NOT merge by themselves: lanes re-walk different
+//                      segments in parallel here instead of one serial chase per group.)
+//                      The groups themselves are resolved by the same relaxation one level up
+//                      (k_group_scatter / k_group_apply, one kernel pair per round; group 0's
+//                      entry is known).  Keeping dead groups talking matters: when a
+//                      mis-speculated "long literal" wrongly kills a run of groups they all
+//                      come back in the round after it is corrected instead of one per round.
+//                      Runs of incompressible blocks are chains of maximal literals that can
+//                      only be found one from the other; k_group_scatter looks 24 of them ahead.
+//                      An adversarial stream degrades to sequential but stays correct.
 //   C  (k_group_final) every live segment sums the output bytes of its elements and stores the
 //                      exact bit map of its element starts (for the segment-driven decoder)
 //      k_scan_*        exclusive scan -> output offset of every segment
@@ -144,34 +145,6 @@ __global__ void __launch_bounds__(256) k_index_spec(const uint8_t *__restrict__ 
     const uint64_t x = walk(body, body_len, lo, hi, lo, nullptr, p, merged);
     paths[t] = make_uint4(p.bits[0], p.bits[1], p.bits[2], p.bits[3]);
     exits[t] = x;
-}
-
-// A': where the walk of segment t-1 lands in segment t, that offset is (in converged regions)
-// the true entry of t, but it usually lies before the point where t's own speculative walk
-// merged into the chain.  Walk from it until t's path is met and add those offsets to the
-// path, so that the group chase below finds the chain "on path" in every such segment.
-__global__ void __launch_bounds__(256) k_index_link(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
-                                                    uint4 *__restrict__ paths, const uint64_t *__restrict__ exits)
-{
-    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (t == 0 || t >= nseg)
-        return;
-    const uint64_t x = exits[t - 1];
-    const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
-    if (x < lo || x >= hi)
-        return;
-    const uint4 pv = paths[t];
-    Path p;
-    p.bits[0] = pv.x, p.bits[1] = pv.y, p.bits[2] = pv.z, p.bits[3] = pv.w;
-    if (p.test((uint32_t)(x - lo)))
-        return;
-    Path fresh;
-    fresh.clear();
-    bool merged;
-    (void)walk(body, body_len, lo, hi, x, &p, fresh, merged);
-    if (merged)
-        paths[t] = make_uint4(p.bits[0] | fresh.bits[0], p.bits[1] | fresh.bits[1], p.bits[2] | fresh.bits[2],
-                              p.bits[3] | fresh.bits[3]);
 }
 
 // ---- groups of kGroup segments ------------------------------------------------------------
@@ -813,10 +786,9 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
     const unsigned ggrid = (unsigned)((ngroup + 127) / 128);                       // one thread per group
     const unsigned wgrid = (unsigned)((ngroup + kGroupCta / 32 - 1) / (kGroupCta / 32)); // one warp per group
     k_index_spec<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits);
-    k_index_link<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits);
     k_group_init<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.g_exit, w.g_vis,
                                         w.claim);
-    *launches += 3;
+    *launches += 2;
     // The "did anything change" flags are only read back every few rounds (4, then 8, 16, ... 64):
     // a round costs two short kernels, a host round trip costs more.
     constexpr uint32_t kMaxBatch = 64;
