@@ -127,7 +127,7 @@ class ClockSampler:
             for name, v in zip(names, r[3:7]):
                 if v.strip().lower().startswith("active"):
                     reasons.add(name)
-        busy = [v for v in sm if v >= 0.5 * max(sm)] if sm else []
+        busy = [v for v in sm if v >= 0.5 * max(smax)] if sm else []
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(smax) if smax else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -257,14 +257,13 @@ def run_gpu_arm(args) -> None:
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         launches0 = api.launch_count()
         barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_start.record()
         for i in range(args.steps):
             step(evs[i])
         t_end.record()
         barrier()
-        clocks = sampler.stop() if sampler else None
+        clocks = None
         total_ms = t_start.elapsed_time(t_end)
         try:
             kern_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
@@ -273,6 +272,11 @@ def run_gpu_arm(args) -> None:
         return {"total_ms": max_over_ranks(total_ms), "kernel_ms": kern_ms, "clocks": clocks,
                 "launches": api.launch_count() - launches0, "kernel": kernel_name}
 
+    # clocks are sampled over the whole measured section (the timed regions themselves last
+    # tens of milliseconds, less than nvidia-smi needs to start); idle samples are dropped
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(1.0)
     td = timed(step_decompress, "k_decode_seg")
     codec.check_status()
     assert torch.equal(out, data), "round trip failed (pipelined path)"
@@ -280,7 +284,7 @@ def run_gpu_arm(args) -> None:
     codec.check_status()
     td["kernel_ms"] = tk["kernel_ms"]
     td["unpipelined_ms_per_step"] = tk["total_ms"] / args.steps
-    tc = timed(step_compress, "k_compress<hash> + k_scan_sizes + k_gather")
+    tc = timed(step_compress, "k_parse<hash> (+ k_emit + k_scan_sizes + k_gather)")
     codec.check_status()
 
     # ---- end to end through the host-buffer C-ABI (pinned host memory, copies inside)
@@ -318,15 +322,27 @@ def run_gpu_arm(args) -> None:
     dt_c = e2e(e2e_comp)
     assert got["c"].size == c_bytes and torch.equal(h_comp[:c_bytes], h_stream), "e2e stream differs"
 
+    clocks = sampler.stop() if sampler else None
+    td["clocks"] = tc["clocks"] = clocks
+
     # ---- aggregate over ranks
     total_u = sum_over_ranks(float(n))
     total_c = sum_over_ranks(float(c_bytes))
     peak, peak_src = measured_peak()
 
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        traffic = {}
+
     def roofline(t, per_launch_bytes):
         achieved = per_launch_bytes / (t["kernel_ms"] * 1e-3) / 1e9
+        tr = traffic.get(t["kernel"].split()[0])
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": t["kernel"],
+                "traffic": tr["dram_bytes_per_launch"] if tr and n == tr.get("bytes_per_gpu") else None,
+                "traffic_source": tr.get("source") if tr else None,
+                "peak_source": peak_src, "kernel": t["kernel"],
                 "algorithmic_bytes_per_launch": per_launch_bytes, "kernel_ms": t["kernel_ms"]}
 
     if rank == 0:

@@ -207,3 +207,34 @@ def test_cli_roundtrip(tmp_path, oracle):
     assert snp.read_bytes() == oracle.compress(data, 0).tobytes()
     assert bsn.read_bytes() == oracle.compress(data, 1).tobytes()
     assert dec.read_bytes() == data.tobytes()
+
+
+def test_config0_reference_cli_64mib_text(tmp_path):
+    """BASELINE.json configs[0]: the reference's own command line (oracle/_ref/snappy_ref, built
+    unmodified from /root/reference/src) against ours on a 64 MiB text-like file: `-c` streams
+    must be byte-identical, each decoder must invert the other's stream."""
+    import subprocess
+    import oracle_lib
+    if not os.path.exists(oracle_lib.REF_BIN):
+        pytest.skip("oracle/_ref/snappy_ref not built")
+    data = corpus.make_corpus("text", 64 << 20, device="cuda").cpu().numpy()
+    src = tmp_path / "text64.bin"
+    src.write_bytes(data.tobytes())
+    ours, theirs = tmp_path / "ours.snp", tmp_path / "ref.snp"
+    subprocess.run([api.CLI_PATH, "-c", str(src), str(ours)], check=True)
+    subprocess.run([oracle_lib.REF_BIN, "-c", str(src), str(theirs)], check=True)
+    a, b = np.fromfile(ours, np.uint8), np.fromfile(theirs, np.uint8)
+    _assert_same(a, b, "CLI -c stream vs reference CLI")
+    # our decoder on the reference's stream, the reference's decoder on ours
+    subprocess.run([api.CLI_PATH, "-d", str(theirs), str(tmp_path / "ours.dec")], check=True)
+    _assert_same(np.fromfile(tmp_path / "ours.dec", np.uint8), data, "our -d on the reference stream")
+    subprocess.run([oracle_lib.REF_BIN, "-d", str(ours), str(tmp_path / "ref.dec")], check=True)
+    _assert_same(np.fromfile(tmp_path / "ref.dec", np.uint8), data, "reference -d on our stream")
+    # BST path: same size (and in fact the same bytes) as the reference's -b
+    subprocess.run([api.CLI_PATH, "-b", str(src), str(tmp_path / "ours.bsnp")], check=True)
+    small = tmp_path / "text8.bin"
+    small.write_bytes(data[: 8 << 20].tobytes())
+    subprocess.run([api.CLI_PATH, "-b", str(small), str(tmp_path / "ours8.bsnp")], check=True)
+    subprocess.run([oracle_lib.REF_BIN, "-b", str(small), str(tmp_path / "ref8.bsnp")], check=True)
+    _assert_same(np.fromfile(tmp_path / "ours8.bsnp", np.uint8), np.fromfile(tmp_path / "ref8.bsnp", np.uint8),
+                 "CLI -b stream vs reference CLI")
