@@ -136,10 +136,16 @@ __device__ __forceinline__ uint32_t single_element(const uint8_t *__restrict__ i
     return 0;
 }
 
-// Produces T output bytes at out[op ..) from the ne elements in `elems`
-// ({window-relative start, len, literal flag | info, 2^16/offset+1 or 0}).
-__device__ __forceinline__ void produce(const uint8_t *__restrict__ in, uint8_t *out, uint32_t op, uint32_t T,
-                                        const uint4 *elems, uint32_t ne, uint32_t lane)
+// Produces T output bytes at out[op ..) from the ne elements in `elems`:
+//   x = window-relative start, y = offset (0: literal) | (floor(2^15/offset)+1) << 16 when the copy
+//   overlaps itself, (z,w) = pointer p such that byte k of the window is p[k] -- the stream for a
+//   literal, out + op - offset for a copy.
+// In every round the lane that produces output byte k finds its element from a bit map of the
+// element starts inside the round (rank = #elements before the round + popc(map up to k) - 1).
+// A copy whose source byte is produced by the very same round is followed back through the
+// round's elements until it leaves the round or lands in a literal.
+__device__ __forceinline__ void produce(uint8_t *out, uint32_t op, uint32_t T, const uint4 *elems, uint32_t ne,
+                                        uint32_t lane)
 {
     const uint32_t my_start = lane < ne ? elems[lane].x : 0xffffffffu;
     for (uint32_t c = 0; c < T; c += 32) {
@@ -153,21 +159,19 @@ __device__ __forceinline__ void produce(const uint8_t *__restrict__ in, uint8_t 
             if (pending) {
                 const uint32_t r = before + __popc(B & (0xffffffffu >> (31u - (k - c)))) - 1u;
                 const uint4 e = elems[r];
-                const uint32_t i = k - e.x;
-                if (e.z & 0x80000000u) {
-                    val = __ldg(in + (e.z & 0x7fffffffu) + i); // write_literal :232-239
+                const uint32_t off = e.y & 0xffffu, inv = e.y >> 16;
+                uint32_t kk = k;
+                if (inv) { // write_copy :273-280: byte i comes from i mod offset when the copy overlaps itself
+                    const uint32_t i = k - e.x;
+                    kk = e.x + i - off * ((i * inv) >> 15);
+                }
+                if (off == 0 || kk < c + off) {
+                    // a literal, or a copy whose source was written by an earlier step / round
+                    const uint8_t *p = reinterpret_cast<const uint8_t *>(((uint64_t)e.w << 32) | e.z);
+                    val = p[kk];
                     pending = false;
                 } else {
-                    const uint32_t off = e.z;
-                    // write_copy :273-280: byte i comes from i mod offset when the copy overlaps itself
-                    const uint32_t s = e.w ? i - off * ((i * e.w) >> 16) : i;
-                    const uint32_t src = op + e.x + s - off; // block-relative, >= 0 (checked by the caller)
-                    if (src < op + c) {
-                        val = out[src]; // written by an earlier step or an earlier round
-                        pending = false;
-                    } else {
-                        k = src - op; // produced by this very round: follow it back
-                    }
+                    k = kk - off; // produced by this very round: follow it back
                 }
             }
         } while (__any_sync(kFull, pending));
@@ -204,12 +208,20 @@ __device__ __forceinline__ uint32_t run_step(const uint8_t *__restrict__ in, uin
     if (BC | BF)
         return BC ? SNAPPY_B200_ST_CORRUPT : SNAPPY_B200_ST_FRAMING;
     if (mine) {
-        // small offsets repeat their pattern (offset < length): keep 2^16/offset for "i mod offset"
-        const uint32_t inv = (!h.is_lit && h.info < h.len) ? 65536u / h.info + 1u : 0u;
-        elems[rank] = make_uint4(start, h.len, h.info | (h.is_lit ? 0x80000000u : 0u), inv);
+        uint32_t y = 0;
+        const uint8_t *p;
+        if (h.is_lit) {
+            p = in + h.info - start; // byte k of the window = stream byte info + (k - start)
+        } else {
+            const uint32_t off = h.info; // <= 65535 here (copy-4 takes the one-element path)
+            y = off | (off < h.len ? (32768u / off + 1u) << 16 : 0u);
+            p = out + op - off; // byte k of the window = output byte op + k - off
+        }
+        const uint64_t pa = reinterpret_cast<uint64_t>(p);
+        elems[rank] = make_uint4(start, y, (uint32_t)pa, (uint32_t)(pa >> 32));
     }
     __syncwarp(); // also: stores of earlier steps are visible to every lane from here
-    produce(in, out, op, T, elems, ne, lane);
+    produce(out, op, T, elems, ne, lane);
     op += T;
     return 0;
 }
@@ -265,7 +277,8 @@ __global__ void __launch_bounds__(32) k_decode_seg(const uint8_t *__restrict__ s
         const uint4 sv = __ldg(starts + t);
         uint32_t R[4] = {sv.x, sv.y, sv.z, sv.w};
         const uint32_t seg_lo = (uint32_t)((t - t0) * kSegBytes);
-        // keep only the starts that belong to this block
+        // keep only the starts that belong to this block (only the first / last segment can hold others)
+        if (t == t0 || t == t1)
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             const uint32_t lo = seg_lo + 32 * w; // stream position of bit 0 of this word
