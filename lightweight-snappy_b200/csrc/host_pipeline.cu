@@ -11,7 +11,7 @@
 //               blocks (the first one also carries the varint of the whole input); its size is
 //               read back, which tells where the chunk goes in the caller's buffer, and its
 //               bytes follow on the download stream.
-//   decompress  the stream is uploaded in 192 MiB pieces.  Whenever a piece has landed, K0 runs
+//   decompress  the stream is uploaded in pieces that grow from 24 to 192 MiB.  Whenever a piece has landed, K0 runs
 //               on the not-yet-decoded tail of what is on the device ("open-ended": the
 //               element cut off by the end of the piece is not an error); every block that is
 //               complete is decoded by the segment-driven decoder on a second stream (so it
@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -106,9 +107,16 @@ struct HostCtx {
             cap[i] = bytes;
         return e;
     }
+    int device = -1;
     cudaError_t init()
     {
-        cudaError_t e = cudaSuccess;
+        int dev = -1;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess)
+            return e;
+        if (device != -1 && dev != device)
+            release(); // the cached streams / buffers belong to another device
+        device = dev;
         for (cudaStream_t *s : {&s_up, &s_run, &s_down, &s_dec, &s_slot[0], &s_slot[1], &s_slot[2], &s_slot[3]})
             if (e == cudaSuccess && !*s)
                 e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
@@ -121,6 +129,7 @@ struct HostCtx {
     }
     void release()
     {
+        device = -1;
         for (int i = 0; i < kBufs; ++i) {
             if (buf[i])
                 cudaFree(buf[i]);
@@ -178,8 +187,8 @@ uint64_t piece_region_cap(uint64_t stream_bytes, uint64_t piece)
 // block that is complete, on a second stream so that it overlaps K0 of the next piece.
 // Returns a SNAPPY_B200_* code; the last decode may still be in flight on r.s_dec.
 int decode_pieces(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t hdr, uint64_t total, uint8_t *d_out,
-                  uint64_t *d_abs_offsets, uint32_t *d_status, uint64_t piece, const PieceResources &r,
-                  const PieceHooks &hooks)
+                  uint64_t *d_abs_offsets, uint32_t *d_status, const std::vector<uint64_t> &piece_end,
+                  uint64_t region_cap, const PieceResources &r, const PieceHooks &hooks)
 {
 #define CUP(call, what)                                                                                                \
     do {                                                                                                               \
@@ -191,14 +200,13 @@ int decode_pieces(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t hdr, 
         }                                                                                                              \
     } while (0)
     const uint64_t nb = (total + kBlock - 1) / kBlock;
-    const uint64_t n_pieces = (stream_bytes + piece - 1) / piece;
-    const uint64_t region_cap = piece_region_cap(stream_bytes, piece);
+    const uint64_t n_pieces = piece_end.size();
     uint64_t rs = hdr; // stream offset of the first block that is not decoded yet
     uint64_t ob = 0;   // blocks decoded so far
     uint64_t launches = 0, used = 0;
     for (uint64_t p = 0; p < n_pieces; ++p) {
         const bool last = p + 1 == n_pieces;
-        const uint64_t hi = std::min((p + 1) * piece, stream_bytes);
+        const uint64_t hi = piece_end[p];
         if (hooks.before_piece)
             CUP(hooks.before_piece(p, r.s_run), "stream wait");
         if (hi <= rs)
@@ -408,10 +416,17 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     CU(g_ctx.init(), "context init");
     const uint64_t nb = (total + kBlock - 1) / kBlock;
+    // pieces grow from 1/8 of the full size: the first download starts early, the later pieces are
+    // large enough to amortise K0's fixed cost and to fill the GPU
     const uint64_t piece = kUploadPiece;
-    const uint64_t n_pieces = (stream_bytes + piece - 1) / piece;
+    std::vector<uint64_t> piece_end;
+    for (uint64_t at = 0, len = std::max<uint64_t>(piece / 8, 1 << 20); at < stream_bytes; len = std::min(len * 2, piece)) {
+        at = std::min(at + len, stream_bytes);
+        piece_end.push_back(at);
+    }
+    const uint64_t n_pieces = piece_end.size();
     // a K0 region is at most one piece plus the carried-over incomplete block
-    const uint64_t region_cap = std::min<uint64_t>(stream_bytes, piece + 2 * (uint64_t)kBlock + 4096);
+    const uint64_t region_cap = piece_region_cap(stream_bytes, piece);
     // buffers: 0 stream, 1 output, 2/3 K0 workspace (alternating), 4/5 block offsets, 6 small
     CU(g_ctx.need(0, stream_bytes + 64), "cudaMalloc");
     CU(g_ctx.need(1, total), "cudaMalloc");
@@ -439,7 +454,7 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
     uint64_t issued = 0; // pieces whose upload has been enqueued (at most 8 ahead of the consumer)
     auto issue_upload = [&]() -> cudaError_t {
         const uint64_t q = issued++;
-        const uint64_t lo = q * piece, len = std::min(piece, stream_bytes - lo);
+        const uint64_t lo = q ? piece_end[q - 1] : 0, len = piece_end[q] - lo;
         cudaError_t e = cudaMemcpyAsync(d_stream + lo, src + lo, len, cudaMemcpyHostToDevice, g_ctx.s_up);
         if (e == cudaSuccess)
             e = cudaEventRecord(ev_up[q & 7], g_ctx.s_up);
@@ -461,7 +476,8 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
             e = cudaMemcpyAsync(dst + first, d_out + first, bytes, cudaMemcpyDeviceToHost, g_ctx.s_down);
         return e;
     };
-    const int rc = decode_pieces(d_stream, stream_bytes, hdr, total, d_out, nullptr, d_status, piece, r, hooks);
+    const int rc = decode_pieces(d_stream, stream_bytes, hdr, total, d_out, nullptr, d_status, piece_end, region_cap, r,
+                                 hooks);
     if (rc != SNAPPY_B200_OK)
         return rc;
     CU(cudaStreamSynchronize(g_ctx.s_dec), "decode");
@@ -519,7 +535,7 @@ int snappy_b200_decompress_device(const uint8_t *d_stream, uint64_t stream_bytes
     r.h_small = g_ctx.h_small + 8;
     PieceHooks hooks; // nothing to wait for, nothing to download
     const int rc = decode_pieces(d_stream, stream_bytes, body_offset, total_out, d_out, d_block_offsets, d_status,
-                                 piece, r, hooks);
+                                 std::vector<uint64_t>{stream_bytes}, piece_region_cap(stream_bytes, piece), r, hooks);
     if (rc != SNAPPY_B200_OK)
         return rc;
     // join: work the caller enqueues next on `stream` sees the decoded output
