@@ -238,3 +238,33 @@ def test_config0_reference_cli_64mib_text(tmp_path):
     subprocess.run([oracle_lib.REF_BIN, "-b", str(small), str(tmp_path / "ref8.bsnp")], check=True)
     _assert_same(np.fromfile(tmp_path / "ours8.bsnp", np.uint8), np.fromfile(tmp_path / "ref8.bsnp", np.uint8),
                  "CLI -b stream vs reference CLI")
+
+
+def test_decoders_on_random_valid_streams(oracle):
+    """Element kinds and encodings the compressors never emit (tests/streamgen.py): both decoders
+    and K0 against the oracle decoder."""
+    import torch
+    import streamgen
+    cases = [(s, n, st) for s, (n, st) in enumerate([
+        (1, "mixed"), (100, "mixed"), (4095, "copies"), (65536, "mixed"), (65537, "copies"), (70000, "bigliteral"),
+        (200000, "copies"), (300001, "bigliteral"), (1 << 20, "mixed"), (3 << 20, "copies"), (5 << 20, "bigliteral")])]
+    for seed, total, style in cases:
+        stream, want = streamgen.make_stream(1000 + seed, total, style)
+        assert np.array_equal(oracle.decompress(stream), want)
+        # host API: K0 + segment-driven decoder
+        _assert_same(api.snappy_decompress(stream), want, f"seg decoder {seed} {total} {style}")
+        # window decoder with the oracle's block index
+        offs, _ = oracle.block_index(stream)
+        d_stream = torch.from_numpy(np.concatenate([stream, np.zeros(64, np.uint8)])).cuda()
+        d_offs = torch.from_numpy(offs.astype(np.int64)).cuda()
+        out = torch.zeros(total, dtype=torch.uint8, device="cuda")
+        codec = api.DeviceCodec(max(total, 1 << 16))
+        codec.decompress_indexed(d_stream, d_offs, total, out)
+        codec.check_status()
+        _assert_same(out.cpu().numpy(), want, f"window decoder {seed} {total} {style}")
+        # K0 block offsets
+        hdr = stream.size - (offs[-1] - offs[0]) if False else int(offs[0])
+        got_offs = torch.zeros(len(offs), dtype=torch.int64, device="cuda")
+        codec.index(d_stream, stream.size, hdr, total, got_offs)
+        codec.check_status()
+        assert np.array_equal(got_offs.cpu().numpy().astype(np.uint64), offs), f"K0 offsets {seed}"
