@@ -181,7 +181,79 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
     const uint32_t odd = lane & 1u; // odd lanes are the probes
     const unsigned vis_mask = lane >= 1 ? (1u << (lane - 1)) - 1u : 0u; // events a probe may see
 
+    const uint32_t hl = (lane + 1) >> 1; // stride-1 layout: event position = pos - 1 + hl
+
     for (;;) {
+        // ---- fast path of the hash parse: all 16 probes one byte apart (skip + 15 < 64) and none
+        // of them near the end of the block.  Same events, same rules as the general step below,
+        // with the positions, the end test and a few shuffles folded away.
+        if (MODE == 0 && skip <= 48u && pos + 34u <= n) {
+            const uint32_t ev = pos - 1u + hl;
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(b) + (ev >> 2);
+            const uint32_t key = __byte_perm(__ldg(wp), __ldg(wp + 1), 0x0123u + 0x1111u * (ev & 3u)); // big-endian
+            const uint32_t prod = key * kHashMul; // hash_bytes :81-84
+            const uint32_t idx = prod >> shift;
+            const uint32_t ph = (prod >> 12) & 0xffu;
+            const unsigned grp = __match_any_sync(kFull, idx);
+            const unsigned vis = grp & vis_mask;
+            const int src = 31 - __clz((int)vis); // latest earlier writer of the slot (-1: none)
+            const uint32_t skey = __shfl_sync(kFull, key, src);
+            const uint32_t nkey = __shfl_down_sync(kFull, key, 8); // my next four bytes
+            const uint32_t tpos = hpos[idx];
+            const uint32_t tfp = hfp[idx];
+            bool hit;
+            uint32_t cand, ext4 = 4;
+            if (vis) {
+                hit = skey == key;
+                cand = pos - 1u + ((uint32_t)(src + 1) >> 1);
+            } else {
+                cand = tpos;
+                hit = false;
+                if (odd && tfp == ph) { // found_match :259-265, and a head start on find_copy_length :61-72
+                    const uint32_t c0 = ld_le32(b, cand, last_word);
+                    const uint32_t c1 = ld_le32(b, cand + 4, last_word);
+                    hit = bswap32(c0) == key;
+                    const uint32_t x = bswap32(c1) ^ nkey;
+                    if (lane < 24 && x)
+                        ext4 = (uint32_t)__clz((int)x) >> 3;
+                }
+            }
+            const unsigned H = __ballot_sync(kFull, odd && hit);
+            if (H == 0) { // 16 misses: update_hash_table :303-307, the last writer of a slot wins
+                if ((grp >> lane) == 1u) {
+                    hpos[idx] = (uint16_t)ev;
+                    hfp[idx] = (uint8_t)ph;
+                }
+                pos += 16;
+                skip += 16;
+                continue;
+            }
+            const int f = __ffs((int)H) - 1;
+            if (((grp & ((1u << (f - 1)) - 1u)) >> lane) == 1u) { // the misses before the cut
+                hpos[idx] = (uint16_t)ev;
+                hfp[idx] = (uint8_t)ph;
+            }
+            __syncwarp();
+            const uint32_t p = pos + ((uint32_t)f >> 1);
+            const uint32_t c = __shfl_sync(kFull, cand, f);
+            const uint32_t e4 = __shfl_sync(kFull, ext4, f);
+            if ((int)lane == f) { // emit_copy :327
+                hpos[idx] = (uint16_t)ev;
+                hfp[idx] = (uint8_t)ph;
+            }
+            const uint32_t len = e4 < 4 ? 4 + e4 : match_extend(b, p, c, n, last_word, lane);
+            if (lane == (nh & 31u))
+                rec = make_uint2(p | ((p - c) << 16), len | ((p - prev_end) << 16));
+            ++nh;
+            if ((nh & 31u) == 0)
+                my_recs[nh - 32 + lane] = rec;
+            pos = p + len;
+            prev_end = pos;
+            skip = 32; // start_new_literal :271-274
+            __syncwarp();
+            continue;
+        }
+
         // ---- lay out 16 probes under the all-miss assumption
         const uint32_t a = skip + D;
         const uint32_t q = a >> 5, r = a & 31u;
