@@ -47,9 +47,8 @@ constexpr uint32_t kMaxRecords = 16384; // a copy covers >= 4 bytes
 // Lane l compares bytes [base+4l, base+4l+4) of the two strings; the first lane that sees a
 // difference (or the end of the block) decides.
 __device__ __forceinline__ uint32_t match_extend(const uint8_t *__restrict__ b, uint32_t p, uint32_t c, uint32_t n,
-                                                 uint32_t last_word, uint32_t lane)
+                                                 uint32_t last_word, uint32_t lane, uint32_t base = 4)
 {
-    uint32_t base = 4;
     uint32_t width = 8; // most matches are short: first look at 32 bytes, then 128 at a time
     for (;;) {
         uint32_t t = 4; // number of equal bytes in this lane's word; 4 = keep going
@@ -198,11 +197,15 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
             const unsigned vis = grp & vis_mask;
             const int src = 31 - __clz((int)vis); // latest earlier writer of the slot (-1: none)
             const uint32_t skey = __shfl_sync(kFull, key, src);
-            const uint32_t nkey = __shfl_down_sync(kFull, key, 8); // my next four bytes
+            // my next 12 bytes are the keys of the lanes 8, 16 and 24 up (two lanes per byte step)
+            const uint32_t nk1 = __shfl_down_sync(kFull, key, 8);
+            const uint32_t nk2 = __shfl_down_sync(kFull, key, 16);
+            const uint32_t nk3 = __shfl_down_sync(kFull, key, 24);
             const uint32_t tpos = hpos[idx];
             const uint32_t tfp = hfp[idx];
             bool hit;
-            uint32_t cand, ext4 = 4;
+            uint32_t cand;
+            uint32_t ext = 0x100; // bit 8: the match may go on past the bytes compared here (low bits: how many)
             if (vis) {
                 hit = skey == key;
                 cand = pos - 1u + ((uint32_t)(src + 1) >> 1);
@@ -210,12 +213,31 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
                 cand = tpos;
                 hit = false;
                 if (odd && tfp == ph) { // found_match :259-265, and a head start on find_copy_length :61-72
-                    const uint32_t c0 = ld_le32(b, cand, last_word);
-                    const uint32_t c1 = ld_le32(b, cand + 4, last_word);
-                    hit = bswap32(c0) == key;
-                    const uint32_t x = bswap32(c1) ^ nkey;
-                    if (lane < 24 && x)
-                        ext4 = (uint32_t)__clz((int)x) >> 3;
+                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(b) + (cand >> 2);
+                    const uint32_t sh = (cand & 3u) * 8u;
+                    // cand + 19 < pos + 19 < n: all five words are inside the block
+                    const uint32_t w0 = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2), w3 = __ldg(cw + 3),
+                                   w4 = __ldg(cw + 4);
+                    hit = bswap32(__funnelshift_r(w0, w1, sh)) == key;
+                    const uint32_t x1 = bswap32(__funnelshift_r(w1, w2, sh)) ^ nk1;
+                    const uint32_t x2 = bswap32(__funnelshift_r(w2, w3, sh)) ^ nk2;
+                    const uint32_t x3 = bswap32(__funnelshift_r(w3, w4, sh)) ^ nk3;
+                    // big-endian words: leading equal bytes.  Lanes too high to have neighbours
+                    // 8 / 16 / 24 up stop at what they can see and leave the rest to match_extend.
+                    if (lane >= 24)
+                        ext = 0x100;
+                    else if (x1)
+                        ext = (uint32_t)__clz((int)x1) >> 3;
+                    else if (lane >= 16)
+                        ext = 0x104;
+                    else if (x2)
+                        ext = 4 + ((uint32_t)__clz((int)x2) >> 3);
+                    else if (lane >= 8)
+                        ext = 0x108;
+                    else if (x3)
+                        ext = 8 + ((uint32_t)__clz((int)x3) >> 3);
+                    else
+                        ext = 0x10c;
                 }
             }
             const unsigned H = __ballot_sync(kFull, odd && hit);
@@ -236,12 +258,12 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
             __syncwarp();
             const uint32_t p = pos + ((uint32_t)f >> 1);
             const uint32_t c = __shfl_sync(kFull, cand, f);
-            const uint32_t e4 = __shfl_sync(kFull, ext4, f);
+            const uint32_t ex = __shfl_sync(kFull, ext, f);
             if ((int)lane == f) { // emit_copy :327
                 hpos[idx] = (uint16_t)ev;
                 hfp[idx] = (uint8_t)ph;
             }
-            const uint32_t len = e4 < 4 ? 4 + e4 : match_extend(b, p, c, n, last_word, lane);
+            const uint32_t len = ex < 0x100 ? 4 + ex : match_extend(b, p, c, n, last_word, lane, 4 + (ex & 0xffu));
             if (lane == (nh & 31u))
                 rec = make_uint2(p | ((p - c) << 16), len | ((p - prev_end) << 16));
             ++nh;
