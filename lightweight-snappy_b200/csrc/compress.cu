@@ -181,12 +181,65 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
     const unsigned vis_mask = lane >= 1 ? (1u << (lane - 1)) - 1u : 0u; // events a probe may see
 
     const uint32_t hl = (lane + 1) >> 1; // stride-1 layout: event position = pos - 1 + hl
+    bool narrow = false;                 // the last probe hit at once: try the first probe alone
 
     for (;;) {
         // ---- fast path of the hash parse: all 16 probes one byte apart (skip + 15 < 64) and none
         // of them near the end of the block.  Same events, same rules as the general step below,
         // with the positions, the end test and a few shuffles folded away.
         if (MODE == 0 && skip <= 48u && pos + 34u <= n) {
+            if (narrow) {
+                // The last probe hit at once.  Runs (and repeated phrases) keep doing that, so try
+                // the first probe alone with warp-uniform work -- no event layout, no match, no
+                // ballot.  On a miss nothing has been changed and the full step below takes over.
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(b) + (pos >> 2);
+                const uint32_t psh = (pos & 3u) * 8u;
+                const uint32_t k0 = __ldg(wp), k1 = __ldg(wp + 1), k2 = __ldg(wp + 2), k3 = __ldg(wp + 3),
+                               k4 = __ldg(wp + 4); // pos + 19 < n
+                const uint32_t key = bswap32(__funnelshift_r(k0, k1, psh));
+                const uint32_t prod = key * kHashMul;
+                const uint32_t idx = prod >> shift;
+                const uint32_t ph = (prod >> 12) & 0xffu;
+                const uint32_t cand = hpos[idx];
+                bool hit = false;
+                uint32_t ext = 0;
+                if (hfp[idx] == ph) {
+                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(b) + (cand >> 2);
+                    const uint32_t sh = (cand & 3u) * 8u;
+                    const uint32_t w0 = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2), w3 = __ldg(cw + 3),
+                                   w4 = __ldg(cw + 4);
+                    hit = __funnelshift_r(w0, w1, sh) == __funnelshift_r(k0, k1, psh);
+                    const uint32_t x1 = __funnelshift_r(w1, w2, sh) ^ __funnelshift_r(k1, k2, psh);
+                    const uint32_t x2 = __funnelshift_r(w2, w3, sh) ^ __funnelshift_r(k2, k3, psh);
+                    const uint32_t x3 = __funnelshift_r(w3, w4, sh) ^ __funnelshift_r(k3, k4, psh);
+                    // little-endian words: trailing equal bytes
+                    ext = x1   ? (uint32_t)(__ffs((int)x1) - 1) >> 3
+                          : x2 ? 4 + ((uint32_t)(__ffs((int)x2) - 1) >> 3)
+                          : x3 ? 8 + ((uint32_t)(__ffs((int)x3) - 1) >> 3)
+                               : 0x10c;
+                }
+                if (hit) {
+                    __syncwarp();
+                    if (lane == 0) { // emit_copy :327
+                        hpos[idx] = (uint16_t)pos;
+                        hfp[idx] = (uint8_t)ph;
+                    }
+                    const uint32_t p = pos;
+                    const uint32_t len =
+                        ext < 0x100 ? 4 + ext : match_extend(b, p, cand, n, last_word, lane, 4 + (ext & 0xffu));
+                    if (lane == (nh & 31u))
+                        rec = make_uint2(p | ((p - cand) << 16), len | ((p - prev_end) << 16));
+                    ++nh;
+                    if ((nh & 31u) == 0)
+                        my_recs[nh - 32 + lane] = rec;
+                    pos = p + len;
+                    prev_end = pos;
+                    skip = 32;
+                    __syncwarp();
+                    continue;
+                }
+                narrow = false;
+            }
             const uint32_t ev = pos - 1u + hl;
             const uint32_t *wp = reinterpret_cast<const uint32_t *>(b) + (ev >> 2);
             const uint32_t key = __byte_perm(__ldg(wp), __ldg(wp + 1), 0x0123u + 0x1111u * (ev & 3u)); // big-endian
@@ -272,6 +325,7 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
             pos = p + len;
             prev_end = pos;
             skip = 32; // start_new_literal :271-274
+            narrow = f == 1;
             __syncwarp();
             continue;
         }
