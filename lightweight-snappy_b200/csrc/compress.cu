@@ -6,12 +6,7 @@
 // and the element encodings of src/snappy_compression.c:95-165.  How it is computed is not.
 //
 // k_parse -- one warp per 64 KiB block; the serial part, kept as lean as possible.
-// While the probes are one byte apart (the usual state: the stride only grows after 32 misses
-// in a row) the hash parse simply runs the reference's loop with warp-uniform work: after a
-// copy every ~4 probes (text) or every probe (runs) there is nothing for speculation to win,
-// and a miss costs only an L1 key load and two shared-memory accesses.  Elsewhere -- sparse
-// probing through incompressible data, block ends, the exact-key mode -- the warp speculates:
-// the parse is serial in the table state, so each step lays the next 16
+// The parse is serial in the table state, so the warp speculates.  Each step lays the next 16
 // probe positions out as 32 "events" (lane 2j = the p-1 insertion that probe j would make on
 // a miss, lane 2j+1 = probe j itself), under the assumption that every earlier probe of the
 // step misses.  Lanes look their key up in the shared-memory table AND in the earlier lanes
@@ -185,47 +180,51 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
     const uint32_t odd = lane & 1u; // odd lanes are the probes
     const unsigned vis_mask = lane >= 1 ? (1u << (lane - 1)) - 1u : 0u; // events a probe may see
 
-    bool prev_fresh = false; // hash mode: position pos - 1 is in the table with its current key
+    const uint32_t hl = (lane + 1) >> 1; // stride-1 layout: event position = pos - 1 + hl
+    bool narrow = false;                 // the last probe hit at once: try the first probe alone
 
     for (;;) {
-        // ---- hash parse, probes one byte apart (32 <= skip < 64) and not near the end of the
-        // block: the reference's own loop, one probe at a time, with warp-uniform work.  A miss
-        // costs a key load that hits L1, two shared-memory reads and two writes (~100 cycles of
-        // dependent latency), far less than a 16-wide speculative step -- and with a copy every
-        // ~4 probes on text and every probe on runs there is little for speculation to win.
-        // Every lane computes and stores the same values, so no warp synchronisation is needed.
-        if (MODE == 0) {
-            while (skip < 64u && pos + 20u <= n) {
+        // ---- fast path of the hash parse: all 16 probes one byte apart (skip + 15 < 64) and none
+        // of them near the end of the block.  Same events, same rules as the general step below,
+        // with the positions, the end test and a few shuffles folded away.
+        if (MODE == 0 && skip <= 48u && pos + 34u <= n) {
+            if (narrow) {
+                // First probe after a copy.  Runs and repeated phrases hit again at once (every
+                // time on low-entropy data, one time in four on text), so try that probe alone
+                // with warp-uniform work -- no event layout, no match, no ballot.  On a miss
+                // nothing has been changed and the full step below takes over.
                 const uint32_t *wp = reinterpret_cast<const uint32_t *>(b) + (pos >> 2);
                 const uint32_t psh = (pos & 3u) * 8u;
-                const uint32_t k0 = __ldg(wp), k1 = __ldg(wp + 1);
-                const uint32_t key = bswap32(__funnelshift_r(k0, k1, psh)); // get_next_u32 :239-241
-                const uint32_t prod = key * kHashMul;                       // hash_bytes :81-84
+                const uint32_t k0 = __ldg(wp), k1 = __ldg(wp + 1), k2 = __ldg(wp + 2), k3 = __ldg(wp + 3),
+                               k4 = __ldg(wp + 4); // pos + 19 < n
+                const uint32_t key = bswap32(__funnelshift_r(k0, k1, psh));
+                const uint32_t prod = key * kHashMul;
                 const uint32_t idx = prod >> shift;
                 const uint32_t ph = (prod >> 12) & 0xffu;
                 const uint32_t cand = hpos[idx];
                 bool hit = false;
                 uint32_t ext = 0;
-                if (hfp[idx] == ph) { // found_match :259-265, and a head start on find_copy_length :61-72
+                if (hfp[idx] == ph) {
                     const uint32_t *cw = reinterpret_cast<const uint32_t *>(b) + (cand >> 2);
                     const uint32_t sh = (cand & 3u) * 8u;
-                    // cand + 19 < pos + 19 < n: all five words of both strings are inside the block
                     const uint32_t w0 = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2), w3 = __ldg(cw + 3),
                                    w4 = __ldg(cw + 4);
-                    const uint32_t k2 = __ldg(wp + 2), k3 = __ldg(wp + 3), k4 = __ldg(wp + 4);
                     hit = __funnelshift_r(w0, w1, sh) == __funnelshift_r(k0, k1, psh);
                     const uint32_t x1 = __funnelshift_r(w1, w2, sh) ^ __funnelshift_r(k1, k2, psh);
                     const uint32_t x2 = __funnelshift_r(w2, w3, sh) ^ __funnelshift_r(k2, k3, psh);
                     const uint32_t x3 = __funnelshift_r(w3, w4, sh) ^ __funnelshift_r(k3, k4, psh);
-                    // little-endian words: trailing equal bytes; 0x100 = goes on past these 12
+                    // little-endian words: trailing equal bytes
                     ext = x1   ? (uint32_t)(__ffs((int)x1) - 1) >> 3
                           : x2 ? 4 + ((uint32_t)(__ffs((int)x2) - 1) >> 3)
                           : x3 ? 8 + ((uint32_t)(__ffs((int)x3) - 1) >> 3)
                                : 0x10c;
                 }
                 if (hit) {
-                    hpos[idx] = (uint16_t)pos; // emit_copy :327
-                    hfp[idx] = (uint8_t)ph;
+                    __syncwarp();
+                    if (lane == 0) { // emit_copy :327
+                        hpos[idx] = (uint16_t)pos;
+                        hfp[idx] = (uint8_t)ph;
+                    }
                     const uint32_t p = pos;
                     const uint32_t len =
                         ext < 0x100 ? 4 + ext : match_extend(b, p, cand, n, last_word, lane, 4 + (ext & 0xffu));
@@ -236,27 +235,100 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
                         my_recs[nh - 32 + lane] = rec;
                     pos = p + len;
                     prev_end = pos;
-                    skip = 32;        // start_new_literal :271-274
-                    prev_fresh = false; // position pos - 1 lies inside the copy: not in the table
-                } else {
-                    // update_hash_table :303-307: p-1 first, then p.  After a miss at p-1 that
-                    // position is already there with the same key, so only the first probe after a
-                    // copy (or at the start of the block) has to add it.
-                    if (!prev_fresh) {
-                        const uint32_t *qp = reinterpret_cast<const uint32_t *>(b) + ((pos - 1) >> 2);
-                        const uint32_t pk = bswap32(__funnelshift_r(__ldg(qp), __ldg(qp + 1), ((pos - 1) & 3u) * 8u));
-                        const uint32_t pprod = pk * kHashMul;
-                        hpos[pprod >> shift] = (uint16_t)(pos - 1);
-                        hfp[pprod >> shift] = (uint8_t)((pprod >> 12) & 0xffu);
-                        prev_fresh = true;
-                    }
-                    hpos[idx] = (uint16_t)pos;
-                    hfp[idx] = (uint8_t)ph;
-                    pos += 1; // append_literal :283-287 (skip >> 5 == 1)
-                    skip += 1;
+                    skip = 32;
+                    __syncwarp();
+                    continue;
+                }
+                narrow = false;
+            }
+            const uint32_t ev = pos - 1u + hl;
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(b) + (ev >> 2);
+            const uint32_t key = __byte_perm(__ldg(wp), __ldg(wp + 1), 0x0123u + 0x1111u * (ev & 3u)); // big-endian
+            const uint32_t prod = key * kHashMul; // hash_bytes :81-84
+            const uint32_t idx = prod >> shift;
+            const uint32_t ph = (prod >> 12) & 0xffu;
+            const unsigned grp = __match_any_sync(kFull, idx);
+            const unsigned vis = grp & vis_mask;
+            const int src = 31 - __clz((int)vis); // latest earlier writer of the slot (-1: none)
+            const uint32_t skey = __shfl_sync(kFull, key, src);
+            // my next 12 bytes are the keys of the lanes 8, 16 and 24 up (two lanes per byte step)
+            const uint32_t nk1 = __shfl_down_sync(kFull, key, 8);
+            const uint32_t nk2 = __shfl_down_sync(kFull, key, 16);
+            const uint32_t nk3 = __shfl_down_sync(kFull, key, 24);
+            const uint32_t tpos = hpos[idx];
+            const uint32_t tfp = hfp[idx];
+            bool hit;
+            uint32_t cand;
+            uint32_t ext = 0x100; // bit 8: the match may go on past the bytes compared here (low bits: how many)
+            if (vis) {
+                hit = skey == key;
+                cand = pos - 1u + ((uint32_t)(src + 1) >> 1);
+            } else {
+                cand = tpos;
+                hit = false;
+                if (odd && tfp == ph) { // found_match :259-265, and a head start on find_copy_length :61-72
+                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(b) + (cand >> 2);
+                    const uint32_t sh = (cand & 3u) * 8u;
+                    // cand + 19 < pos + 19 < n: all five words are inside the block
+                    const uint32_t w0 = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2), w3 = __ldg(cw + 3),
+                                   w4 = __ldg(cw + 4);
+                    hit = bswap32(__funnelshift_r(w0, w1, sh)) == key;
+                    const uint32_t x1 = bswap32(__funnelshift_r(w1, w2, sh)) ^ nk1;
+                    const uint32_t x2 = bswap32(__funnelshift_r(w2, w3, sh)) ^ nk2;
+                    const uint32_t x3 = bswap32(__funnelshift_r(w3, w4, sh)) ^ nk3;
+                    // big-endian words: leading equal bytes.  Lanes too high to have neighbours
+                    // 8 / 16 / 24 up stop at what they can see and leave the rest to match_extend.
+                    if (lane >= 24)
+                        ext = 0x100;
+                    else if (x1)
+                        ext = (uint32_t)__clz((int)x1) >> 3;
+                    else if (lane >= 16)
+                        ext = 0x104;
+                    else if (x2)
+                        ext = 4 + ((uint32_t)__clz((int)x2) >> 3);
+                    else if (lane >= 8)
+                        ext = 0x108;
+                    else if (x3)
+                        ext = 8 + ((uint32_t)__clz((int)x3) >> 3);
+                    else
+                        ext = 0x10c;
                 }
             }
+            const unsigned H = __ballot_sync(kFull, odd && hit);
+            if (H == 0) { // 16 misses: update_hash_table :303-307, the last writer of a slot wins
+                if ((grp >> lane) == 1u) {
+                    hpos[idx] = (uint16_t)ev;
+                    hfp[idx] = (uint8_t)ph;
+                }
+                pos += 16;
+                skip += 16;
+                continue;
+            }
+            const int f = __ffs((int)H) - 1;
+            if (((grp & ((1u << (f - 1)) - 1u)) >> lane) == 1u) { // the misses before the cut
+                hpos[idx] = (uint16_t)ev;
+                hfp[idx] = (uint8_t)ph;
+            }
             __syncwarp();
+            const uint32_t p = pos + ((uint32_t)f >> 1);
+            const uint32_t c = __shfl_sync(kFull, cand, f);
+            const uint32_t ex = __shfl_sync(kFull, ext, f);
+            if ((int)lane == f) { // emit_copy :327
+                hpos[idx] = (uint16_t)ev;
+                hfp[idx] = (uint8_t)ph;
+            }
+            const uint32_t len = ex < 0x100 ? 4 + ex : match_extend(b, p, c, n, last_word, lane, 4 + (ex & 0xffu));
+            if (lane == (nh & 31u))
+                rec = make_uint2(p | ((p - c) << 16), len | ((p - prev_end) << 16));
+            ++nh;
+            if ((nh & 31u) == 0)
+                my_recs[nh - 32 + lane] = rec;
+            pos = p + len;
+            prev_end = pos;
+            skip = 32; // start_new_literal :271-274
+            narrow = true; // (trying the first probe alone costs little even when it then misses)
+            __syncwarp();
+            continue;
         }
 
         // ---- lay out 16 probes under the all-miss assumption
@@ -372,7 +444,6 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
             pos = p + len;
             prev_end = pos;
             skip = 32; // start_new_literal :271-274
-            prev_fresh = false;
             __syncwarp();
         }
 
