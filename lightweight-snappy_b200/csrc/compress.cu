@@ -331,6 +331,29 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
             continue;
         }
 
+        // ---- exact mode, first probe after a copy, tried alone with warp-uniform work (see the
+        // hash-mode single-probe step above; a key that is in the dictionary always hits)
+        if (MODE == 1 && narrow && skip == 32u && pos + 34u <= n) {
+            const uint32_t key = ld_be32(b, pos, last_word);
+            bool found;
+            uint32_t tpos;
+            const uint32_t slot = et.find(b, last_word, key, found, tpos); // found_match_tree tree.c:174-180
+            if (found) {
+                et.tab[slot] = (uint16_t)pos; // tree.c:221 (every lane stores the same value)
+                const uint32_t len = match_extend(b, pos, tpos, n, last_word, lane);
+                if (lane == (nh & 31u))
+                    rec = make_uint2(pos | ((pos - tpos) << 16), len | ((pos - prev_end) << 16));
+                ++nh;
+                if ((nh & 31u) == 0)
+                    my_recs[nh - 32 + lane] = rec;
+                pos += len;
+                prev_end = pos;
+                __syncwarp();
+                continue; // skip stays 32: start_new_literal tree.c:182-186
+            }
+            narrow = false;
+        }
+
         // ---- lay out 16 probes under the all-miss assumption
         const uint32_t a = skip + D;
         const uint32_t q = a >> 5, r = a & 31u;
@@ -444,6 +467,7 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
             pos = p + len;
             prev_end = pos;
             skip = 32; // start_new_literal :271-274
+            narrow = true;
             __syncwarp();
         }
 
