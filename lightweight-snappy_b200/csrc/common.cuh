@@ -35,6 +35,13 @@ __device__ __forceinline__ uint32_t ld_be32(const uint8_t *__restrict__ base, ui
 }
 
 // ---- cooperative byte copy, global -> global, any alignment -------------------------------
+// Ask for a line to be brought into L2.  The parse and decode chains are latency-bound, and the
+// first touch of every input line is otherwise a full DRAM round trip on the critical path.
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // `nt` threads (ids 0..nt-1) copy len bytes.  src is read through the read-only path, so it
 // must not alias anything written by this kernel.  Large copies go in 16-byte destination
 // chunks; the source words are funnel-shifted to the destination alignment.

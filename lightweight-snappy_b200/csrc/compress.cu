@@ -183,7 +183,14 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
     const uint32_t hl = (lane + 1) >> 1; // stride-1 layout: event position = pos - 1 + hl
     bool narrow = false;                 // the last probe hit at once: try the first probe alone
 
+    uint32_t pf = 0; // input prefetched into L2 up to here (4 KiB at a time, 4..8 KiB ahead)
+
     for (;;) {
+        if (pos + 4096u > pf) {
+            if (pf + 128u * lane < n)
+                prefetch_l2(b + pf + 128u * lane);
+            pf += 4096u;
+        }
         // ---- fast path of the hash parse: all 16 probes one byte apart (skip + 15 < 64) and none
         // of them near the end of the block.  Same events, same rules as the general step below,
         // with the positions, the end test and a few shuffles folded away.
@@ -247,52 +254,62 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
             const uint32_t prod = key * kHashMul; // hash_bytes :81-84
             const uint32_t idx = prod >> shift;
             const uint32_t ph = (prod >> 12) & 0xffu;
-            const unsigned grp = __match_any_sync(kFull, idx);
-            const unsigned vis = grp & vis_mask;
-            const int src = 31 - __clz((int)vis); // latest earlier writer of the slot (-1: none)
-            const uint32_t skey = __shfl_sync(kFull, key, src);
             // my next 12 bytes are the keys of the lanes 8, 16 and 24 up (two lanes per byte step)
             const uint32_t nk1 = __shfl_down_sync(kFull, key, 8);
             const uint32_t nk2 = __shfl_down_sync(kFull, key, 16);
             const uint32_t nk3 = __shfl_down_sync(kFull, key, 24);
             const uint32_t tpos = hpos[idx];
             const uint32_t tfp = hfp[idx];
-            bool hit;
-            uint32_t cand;
+            // found_match :259-265 and a head start on find_copy_length :61-72: probes whose
+            // fingerprint agrees fetch the candidate's bytes now, so that the round trip overlaps
+            // the in-step forwarding below (tpos + 19 < pos + 19 < n: all five words are inside)
+            const bool want = odd && tfp == ph;
+            const uint32_t *cw = reinterpret_cast<const uint32_t *>(b) + (tpos >> 2);
+            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;
+            if (want) {
+                w0 = __ldg(cw);
+                w1 = __ldg(cw + 1);
+                w2 = __ldg(cw + 2);
+                w3 = __ldg(cw + 3);
+                w4 = __ldg(cw + 4);
+            }
+            const unsigned grp = __match_any_sync(kFull, idx);
+            const unsigned vis = odd ? grp & vis_mask : 0u;
+            bool hit = false;
+            uint32_t cand = tpos;
             uint32_t ext = 0x100; // bit 8: the match may go on past the bytes compared here (low bits: how many)
-            if (vis) {
-                hit = skey == key;
-                cand = pos - 1u + ((uint32_t)(src + 1) >> 1);
-            } else {
-                cand = tpos;
-                hit = false;
-                if (odd && tfp == ph) { // found_match :259-265, and a head start on find_copy_length :61-72
-                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(b) + (cand >> 2);
-                    const uint32_t sh = (cand & 3u) * 8u;
-                    // cand + 19 < pos + 19 < n: all five words are inside the block
-                    const uint32_t w0 = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2), w3 = __ldg(cw + 3),
-                                   w4 = __ldg(cw + 4);
-                    hit = bswap32(__funnelshift_r(w0, w1, sh)) == key;
-                    const uint32_t x1 = bswap32(__funnelshift_r(w1, w2, sh)) ^ nk1;
-                    const uint32_t x2 = bswap32(__funnelshift_r(w2, w3, sh)) ^ nk2;
-                    const uint32_t x3 = bswap32(__funnelshift_r(w3, w4, sh)) ^ nk3;
-                    // big-endian words: leading equal bytes.  Lanes too high to have neighbours
-                    // 8 / 16 / 24 up stop at what they can see and leave the rest to match_extend.
-                    if (lane >= 24)
-                        ext = 0x100;
-                    else if (x1)
-                        ext = (uint32_t)__clz((int)x1) >> 3;
-                    else if (lane >= 16)
-                        ext = 0x104;
-                    else if (x2)
-                        ext = 4 + ((uint32_t)__clz((int)x2) >> 3);
-                    else if (lane >= 8)
-                        ext = 0x108;
-                    else if (x3)
-                        ext = 8 + ((uint32_t)__clz((int)x3) >> 3);
-                    else
-                        ext = 0x10c;
+            if (__any_sync(kFull, vis != 0u)) {
+                // rare: a probe's slot is written by an earlier event of this same step
+                const int src = 31 - __clz((int)vis); // latest earlier writer of the slot (-1: none)
+                const uint32_t skey = __shfl_sync(kFull, key, src);
+                if (vis) {
+                    hit = skey == key;
+                    cand = pos - 1u + ((uint32_t)(src + 1) >> 1);
                 }
+            }
+            if (vis) {
+            } else if (want) {
+                const uint32_t sh = (tpos & 3u) * 8u;
+                hit = bswap32(__funnelshift_r(w0, w1, sh)) == key;
+                const uint32_t x1 = bswap32(__funnelshift_r(w1, w2, sh)) ^ nk1;
+                const uint32_t x2 = bswap32(__funnelshift_r(w2, w3, sh)) ^ nk2;
+                const uint32_t x3 = bswap32(__funnelshift_r(w3, w4, sh)) ^ nk3;
+                // big-endian words: leading equal bytes.  Lanes too high to have neighbours
+                // 8 / 16 / 24 up stop at what they can see and leave the rest to match_extend.
+                if (lane >= 24)
+                    ext = 0x100;
+                else if (x1)
+                    ext = (uint32_t)__clz((int)x1) >> 3;
+                else if (lane >= 16)
+                    ext = 0x104;
+                else if (x2)
+                    ext = 4 + ((uint32_t)__clz((int)x2) >> 3);
+                else if (lane >= 8)
+                    ext = 0x108;
+                else if (x3)
+                    ext = 8 + ((uint32_t)__clz((int)x3) >> 3);
+                else
+                    ext = 0x10c;
             }
             const unsigned H = __ballot_sync(kFull, odd && hit);
             if (H == 0) { // 16 misses: update_hash_table :303-307, the last writer of a slot wins
