@@ -92,6 +92,34 @@ int status_error(uint32_t st) { return status_to_error(st); }
 size_t compress_workspace_bytes_internal(uint64_t n_bytes) { return compress_ws_bytes(n_bytes); }
 void add_launches(uint64_t n) { g_launches += n; }
 
+// Small device -> host read-backs (sizes, flags, status words).  A cudaMemcpyAsync would queue
+// on the D2H copy engine behind whatever bulk download is in flight (measured: K0 of the next
+// piece waited 6 ms for a 330 MiB download); a one-CTA kernel that stores straight into pinned
+// host memory does not.
+__global__ void k_peek(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, uint32_t n)
+{
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        dst[i] = src[i];
+}
+
+cudaError_t peek_u32(uint32_t *h_pinned_dst, const void *d_src, uint32_t n_u32, cudaStream_t st)
+{
+    k_peek<<<1, 64, 0, st>>>(h_pinned_dst, static_cast<const uint32_t *>(d_src), n_u32);
+    g_launches += 1;
+    return cudaGetLastError();
+}
+
+// 1 KiB of pinned host memory per calling thread (kept for the life of the process).
+uint32_t *thread_pinned_scratch()
+{
+    thread_local uint32_t *p = nullptr;
+    if (!p && cudaHostAlloc(reinterpret_cast<void **>(&p), 1024, cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        p = nullptr;
+    }
+    return p;
+}
+
 // One chunk of a longer input: blocks only, or (first chunk) the varint of the WHOLE input
 // followed by blocks.  Same kernels as snappy_b200_compress_device.
 cudaError_t compress_chunk(const uint8_t *d_in, uint64_t chunk_bytes, uint64_t varint_value, int mode, uint8_t *d_out,

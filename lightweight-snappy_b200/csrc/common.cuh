@@ -35,6 +35,9 @@ __device__ __forceinline__ uint32_t ld_be32(const uint8_t *__restrict__ base, ui
 }
 
 // ---- cooperative byte copy, global -> global, any alignment -------------------------------
+cudaError_t peek_u32(uint32_t *h_pinned_dst, const void *d_src, uint32_t n_u32, cudaStream_t st); // abi.cu
+uint32_t *thread_pinned_scratch();                                                                // abi.cu
+
 // Ask for a line to be brought into L2.  The parse and decode chains are latency-bound, and the
 // first touch of every input line is otherwise a full DRAM round trip on the critical path.
 __device__ __forceinline__ void prefetch_l2(const void *p)

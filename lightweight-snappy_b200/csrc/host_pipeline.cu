@@ -11,7 +11,8 @@
 //               blocks (the first one also carries the varint of the whole input); its size is
 //               read back, which tells where the chunk goes in the caller's buffer, and its
 //               bytes follow on the download stream.
-//   decompress  the stream is uploaded in pieces that grow from 24 to 192 MiB.  Whenever a piece has landed, K0 runs
+//   decompress  the stream is uploaded in pieces that grow from 16 to 128 MiB (measured best on PCIe 5
+//               x16; SNAPPY_B200_PIECE_START_MIB / _GROWTH / _MIB override).  Whenever a piece has landed, K0 runs
 //               on the not-yet-decoded tail of what is on the device ("open-ended": the
 //               element cut off by the end of the piece is not an error); every block that is
 //               complete is decoded by the segment-driven decoder on a second stream (so it
@@ -25,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -58,7 +60,7 @@ uint64_t env_mib(const char *name, uint64_t dflt)
     return (uint64_t)(x > 0 ? x : (long long)dflt) << 20;
 }
 #define kCompressChunk env_mib("SNAPPY_B200_CHUNK_MIB", 128) /* input bytes per compress chunk (whole blocks) */
-#define kUploadPiece env_mib("SNAPPY_B200_PIECE_MIB", 192)   /* stream bytes per upload piece (host path) */
+#define kUploadPiece env_mib("SNAPPY_B200_PIECE_MIB", 128)   /* stream bytes per upload piece (host path) */
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -154,6 +156,43 @@ struct HostCtx {
 
 HostCtx g_ctx;
 
+// SNAPPY_B200_TRACE=1: timeline of a host call (milliseconds since its first enqueue) on stderr.
+struct Trace {
+    bool on = getenv("SNAPPY_B200_TRACE") != nullptr;
+    cudaEvent_t t0 = nullptr;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    void start(cudaStream_t s)
+    {
+        if (!on)
+            return;
+        cudaEventCreate(&t0);
+        cudaEventRecord(t0, s);
+    }
+    void mark(const std::string &what, cudaStream_t s)
+    {
+        if (!on)
+            return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        marks.emplace_back(what, e);
+    }
+    void dump()
+    {
+        if (!on)
+            return;
+        cudaDeviceSynchronize();
+        for (auto &m : marks) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, t0, m.second);
+            fprintf(stderr, "[trace] %8.3f ms  %s\n", ms, m.first.c_str());
+            cudaEventDestroy(m.second);
+        }
+        cudaEventDestroy(t0);
+        marks.clear();
+    }
+};
+
 // Adds `add` to n offsets (K0 reports them relative to the region it was given).
 __global__ void k_rebase_offsets(uint64_t *__restrict__ dst, const uint64_t *__restrict__ src, uint64_t n, uint64_t add)
 {
@@ -167,6 +206,7 @@ struct PieceHooks {
     std::function<cudaError_t(uint64_t p, cudaStream_t s_run)> before_piece;
     // output bytes [first, first + bytes) are final once `done` (recorded on the decode stream) fires
     std::function<cudaError_t(uint64_t first, uint64_t bytes, cudaEvent_t done)> after_decode;
+    Trace *trace = nullptr;
 };
 
 struct PieceResources {
@@ -227,8 +267,10 @@ int decode_pieces(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t hdr, 
                       !last, blocks_left),
             "index launch");
         CUP(cudaEventRecord(r.ev_k0[s], r.s_run), "event record");
-        CUP(cudaMemcpyAsync(r.h_small, index_total(r.ws[s], region), 8, cudaMemcpyDeviceToHost, r.s_run), "read-back");
-        CUP(cudaMemcpyAsync(r.h_small + 1, d_status, 4, cudaMemcpyDeviceToHost, r.s_run), "read-back");
+        if (hooks.trace)
+            hooks.trace->mark("K0 done, piece " + std::to_string(p), r.s_run);
+        CUP(peek_u32(reinterpret_cast<uint32_t *>(r.h_small), index_total(r.ws[s], region), 2, r.s_run), "read-back");
+        CUP(peek_u32(reinterpret_cast<uint32_t *>(r.h_small + 1), d_status, 1, r.s_run), "read-back");
         CUP(cudaStreamSynchronize(r.s_run), "index");
         const uint32_t status = (uint32_t)r.h_small[1];
         if (status) {
@@ -248,7 +290,7 @@ int decode_pieces(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t hdr, 
             continue;
         ++used;
         const uint64_t out_bytes_now = last ? out_left : kdone * kBlock;
-        CUP(cudaMemcpyAsync(r.h_small + 2, r.offs[s] + kdone, 8, cudaMemcpyDeviceToHost, r.s_run), "read-back");
+        CUP(peek_u32(reinterpret_cast<uint32_t *>(r.h_small + 2), r.offs[s] + kdone, 2, r.s_run), "read-back");
         if (d_abs_offsets) {
             k_rebase_offsets<<<(unsigned)((kdone + 1 + 255) / 256), 256, 0, r.s_run>>>(d_abs_offsets + ob, r.offs[s],
                                                                                       kdone + 1, rs);
@@ -260,6 +302,8 @@ int decode_pieces(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t hdr, 
                               d_out + ob * kBlock, d_status, r.s_dec, &launches),
             "decode launch");
         CUP(cudaEventRecord(r.ev_dec[s], r.s_dec), "event record");
+        if (hooks.trace)
+            hooks.trace->mark("decode done, piece " + std::to_string(p) + " (" + std::to_string(out_bytes_now >> 20) + " MiB out)", r.s_dec);
         if (hooks.after_decode)
             CUP(hooks.after_decode(ob * kBlock, out_bytes_now, r.ev_dec[s]), "D2H copy");
         CUP(cudaStreamSynchronize(r.s_run), "read-back");
@@ -347,7 +391,7 @@ int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *
         if (e == cudaSuccess)
             e = cudaEventRecord(ev_run[s], st);
         if (e == cudaSuccess)
-            e = cudaMemcpyAsync(g_ctx.h_small + 4 * s, d_bytes, 16, cudaMemcpyDeviceToHost, st);
+            e = peek_u32(reinterpret_cast<uint32_t *>(g_ctx.h_small + 4 * s), d_bytes, 4, st);
         if (e == cudaSuccess)
             e = cudaEventRecord(ev_size[s], st);
         return e;
@@ -417,10 +461,13 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
     CU(g_ctx.init(), "context init");
     const uint64_t nb = (total + kBlock - 1) / kBlock;
     // pieces grow from 1/8 of the full size: the first download starts early, the later pieces are
-    // large enough to amortise K0's fixed cost and to fill the GPU
+    // large enough to amortise K0's fixed cost and to fill the GPU.  All the small read-backs of
+    // the loop go through peek_u32 so that they never queue behind a download.
     const uint64_t piece = kUploadPiece;
     std::vector<uint64_t> piece_end;
-    for (uint64_t at = 0, len = std::max<uint64_t>(piece / 8, 1 << 20); at < stream_bytes; len = std::min(len * 2, piece)) {
+    const uint64_t growth = std::max<uint64_t>(env_mib("SNAPPY_B200_PIECE_GROWTH", 2) >> 20, 1);
+    for (uint64_t at = 0, len = std::min(piece, env_mib("SNAPPY_B200_PIECE_START_MIB", std::max<uint64_t>(piece >> 23, 1)));
+         at < stream_bytes; len = std::min(len * growth, piece)) {
         at = std::min(at + len, stream_bytes);
         piece_end.push_back(at);
     }
@@ -451,6 +498,8 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
     r.s_run = g_ctx.s_run, r.s_dec = g_ctx.s_dec, r.h_small = g_ctx.h_small;
 
     CU(cudaMemsetAsync(d_status, 0, 4, g_ctx.s_run), "memset");
+    Trace trace;
+    trace.start(g_ctx.s_run);
     uint64_t issued = 0; // pieces whose upload has been enqueued (at most 8 ahead of the consumer)
     auto issue_upload = [&]() -> cudaError_t {
         const uint64_t q = issued++;
@@ -458,6 +507,7 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
         cudaError_t e = cudaMemcpyAsync(d_stream + lo, src + lo, len, cudaMemcpyHostToDevice, g_ctx.s_up);
         if (e == cudaSuccess)
             e = cudaEventRecord(ev_up[q & 7], g_ctx.s_up);
+        trace.mark("upload done, piece " + std::to_string(q) + " (" + std::to_string(len >> 20) + " MiB)", g_ctx.s_up);
         return e;
     };
     while (issued < n_pieces && issued < 8)
@@ -474,16 +524,19 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
         cudaError_t e = cudaStreamWaitEvent(g_ctx.s_down, done, 0);
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(dst + first, d_out + first, bytes, cudaMemcpyDeviceToHost, g_ctx.s_down);
+        trace.mark("download done, " + std::to_string(bytes >> 20) + " MiB", g_ctx.s_down);
         return e;
     };
+    hooks.trace = &trace;
     const int rc = decode_pieces(d_stream, stream_bytes, hdr, total, d_out, nullptr, d_status, piece_end, region_cap, r,
                                  hooks);
     if (rc != SNAPPY_B200_OK)
         return rc;
     CU(cudaStreamSynchronize(g_ctx.s_dec), "decode");
-    CU(cudaMemcpyAsync(g_ctx.h_small + 1, d_status, 4, cudaMemcpyDeviceToHost, g_ctx.s_run), "read-back");
+    CU(peek_u32(reinterpret_cast<uint32_t *>(g_ctx.h_small + 1), d_status, 1, g_ctx.s_run), "read-back");
     CU(cudaStreamSynchronize(g_ctx.s_run), "decode");
     CU(cudaStreamSynchronize(g_ctx.s_down), "D2H copy");
+    trace.dump();
     const uint32_t status = (uint32_t)g_ctx.h_small[1];
     if (status)
         return status_error(status);

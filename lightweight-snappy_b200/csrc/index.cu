@@ -803,8 +803,10 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
                                                        w.g_exit, w.g_vis, w.claim, w.changed + k);
         }
         *launches += 2 * batch;
-        uint32_t changed[kMaxBatch];
-        if ((e = cudaMemcpyAsync(changed, w.changed, 4 * batch, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        uint32_t *changed = thread_pinned_scratch(); // >= kMaxBatch words
+        if (!changed)
+            return cudaErrorMemoryAllocation;
+        if ((e = peek_u32(changed, w.changed, batch, st)) != cudaSuccess ||
             (e = cudaMemsetAsync(w.changed, 0, 4 * kMaxBatch, st)) != cudaSuccess ||
             (e = cudaStreamSynchronize(st)) != cudaSuccess)
             return e;
