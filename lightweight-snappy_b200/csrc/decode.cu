@@ -227,20 +227,60 @@ __device__ __forceinline__ uint32_t run_step(const uint8_t *__restrict__ in, uin
 }
 
 // ------------------------------------------------------------------ segment-driven decoder
-// r-th (0-based) set bit of a 128-bit map.
-__device__ __forceinline__ uint32_t nth_set_bit128(const uint32_t R[4], uint32_t r)
+// One step = one 128-byte stream segment.  Lane l looks at the four start bits of stream bytes
+// 4l..4l+3: an element is at least two bytes long, so at most two elements start there, and
+// the rank of the first one is a popcount of the map below.  All elements of the segment
+// (<= 64) go into the shared-memory table at once; their output offsets come from one warp
+// prefix sum over the per-lane sums.
+constexpr uint32_t kSegElems = 64;
+constexpr uint32_t kRunBytes = kSegElems * 64; // output bytes of a run of ordinary elements (each <= 64)
+
+struct SegSmem {
+    uint4 elems[kSegElems];
+    uint32_t bm[kRunBytes / 32 + 4]; // element starts inside the current run, one bit per output byte
+};
+
+// Produces the output bytes [k_lo, k_hi) (window-relative) of the elements e_lo.. of the table;
+// `bm` holds their starts relative to k_lo.  Same per-byte rule as produce() above.
+__device__ __forceinline__ void produce_run(uint8_t *out, uint32_t op, uint32_t k_lo, uint32_t k_hi, uint32_t e_lo,
+                                            const SegSmem &sm, uint32_t lane)
 {
-    const uint32_t c0 = __popc(R[0]), c1 = c0 + __popc(R[1]), c2 = c1 + __popc(R[2]);
-    const uint32_t w = (r >= c0) + (r >= c1) + (r >= c2);
-    const uint32_t below = w == 0 ? 0u : (w == 1 ? c0 : (w == 2 ? c1 : c2));
-    const uint32_t W = w == 0 ? R[0] : (w == 1 ? R[1] : (w == 2 ? R[2] : R[3]));
-    const uint32_t rr = r - below;
-    uint32_t p = 0;
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1)
-        if ((uint32_t)__popc(W & ((1u << (p + s)) - 1u)) <= rr)
-            p += s;
-    return w * 32 + p;
+    const unsigned le_mask = 0xffffffffu >> (31u - lane);
+    uint32_t before = e_lo; // table index of the first element that starts in this round, if any does
+    uint8_t *o = out + op + k_lo + lane;
+    for (uint32_t c = k_lo; c < k_hi; c += 32, o += 32) {
+        const unsigned B = sm.bm[(c - k_lo) >> 5];
+        uint32_t k = c + lane;
+        bool pending = k < k_hi;
+        uint32_t val = 0;
+        uint32_t r = before + __popc(B & le_mask) - 1u;
+        for (;;) {
+            if (pending) {
+                const uint4 e = sm.elems[r];
+                const uint32_t off = e.y & 0xffffu, inv = e.y >> 16;
+                uint32_t kk = k;
+                if (inv) { // write_copy :273-280: byte i comes from i mod offset when the copy overlaps itself
+                    const uint32_t i = k - e.x;
+                    kk = e.x + i - off * ((i * inv) >> 15);
+                }
+                if (off == 0 || kk < c + off) {
+                    // a literal, or a copy whose source was written by an earlier step / round
+                    const uint8_t *p = reinterpret_cast<const uint8_t *>(((uint64_t)e.w << 32) | e.z);
+                    val = p[kk];
+                    pending = false;
+                } else {
+                    k = kk - off; // produced by this very round: follow it back
+                    r = before + __popc(B & (0xffffffffu >> (31u - (k - c)))) - 1u;
+                }
+            }
+            if (!__any_sync(kFull, pending))
+                break;
+        }
+        if (c + lane < k_hi)
+            *o = (uint8_t)val;
+        before += __popc(B);
+        __syncwarp(); // the next round may read what this one wrote
+    }
 }
 
 __global__ void __launch_bounds__(32) k_decode_seg(const uint8_t *__restrict__ stream, uint64_t body_offset,
@@ -248,7 +288,7 @@ __global__ void __launch_bounds__(32) k_decode_seg(const uint8_t *__restrict__ s
                                                    const uint4 *__restrict__ starts, uint64_t total_out,
                                                    uint8_t *out_base, uint32_t *__restrict__ status)
 {
-    __shared__ uint4 elems[32];
+    __shared__ SegSmem sm;
     const uint32_t lane = threadIdx.x;
     const uint64_t blk = blockIdx.x;
     if (*reinterpret_cast<volatile uint32_t *>(status) != 0)
@@ -271,6 +311,7 @@ __global__ void __launch_bounds__(32) k_decode_seg(const uint8_t *__restrict__ s
     uint8_t *out = out_base + blk * (uint64_t)kBlock;
     const uint64_t oleft = total_out - blk * (uint64_t)kBlock;
     const uint32_t olen = oleft < kBlock ? (uint32_t)oleft : kBlock;
+    const uint32_t w = lane >> 3, sh = (lane & 7u) * 4u; // my nibble of the 128-bit start map
 
     uint32_t op = 0, err = 0;
     for (uint64_t t = t0; t <= t1 && !err; ++t) {
@@ -280,46 +321,141 @@ __global__ void __launch_bounds__(32) k_decode_seg(const uint8_t *__restrict__ s
         // keep only the starts that belong to this block (only the first / last segment can hold others)
         if (t == t0 || t == t1)
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const uint32_t lo = seg_lo + 32 * w; // stream position of bit 0 of this word
-            if (lo + 32 <= first || lo >= lim) {
-                R[w] = 0;
-            } else {
-                if (lo < first)
-                    R[w] &= ~((1u << (first - lo)) - 1u);
-                if (lo + 32 > lim)
-                    R[w] &= (1u << (lim - lo)) - 1u;
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t lo = seg_lo + 32 * q; // stream position of bit 0 of this word
+                if (lo + 32 <= first || lo >= lim) {
+                    R[q] = 0;
+                } else {
+                    if (lo < first)
+                        R[q] &= ~((1u << (first - lo)) - 1u);
+                    if (lo + 32 > lim)
+                        R[q] &= (1u << (lim - lo)) - 1u;
+                }
             }
-        }
-        while ((R[0] | R[1] | R[2] | R[3]) && !err) {
-            const uint32_t cnt = __popc(R[0]) + __popc(R[1]) + __popc(R[2]) + __popc(R[3]);
-            uint32_t ne = min(cnt, 32u);
-            const uint32_t bit = nth_set_bit128(R, min(lane, ne - 1));
-            const uint32_t pos = seg_lo + bit;
-            const uint32_t v = ld_le32_any(in + pos, last_word);
-            const Header h = decode_header(v, pos);
-            const bool special = h.slow || (h.is_lit && h.len >= kLongLiteral);
-            const unsigned S = __ballot_sync(kFull, lane < ne && special);
-            if (S & 1u) {
-                uint32_t ip = __shfl_sync(kFull, pos, 0);
-                const uint32_t v0 = __shfl_sync(kFull, v, 0);
-                err = single_element(in, lim, v0, out, olen, blk, ip, op, lane);
-                ne = 1;
-            } else {
-                if (S)
-                    ne = __ffs((int)S) - 1;
-                err = run_step(in, lim, out, olen, op, lane < ne, lane, ne, h, pos, elems, lane);
-            }
-            // drop the ne starts just consumed
-            const uint32_t lastbit = __shfl_sync(kFull, bit, ne - 1);
+        const uint32_t n0 = __popc(R[0]), n1 = n0 + __popc(R[1]), n2 = n1 + __popc(R[2]), ne = n2 + __popc(R[3]);
+        if (ne == 0)
+            continue;
+        const uint32_t Rw = w == 0 ? R[0] : (w == 1 ? R[1] : (w == 2 ? R[2] : R[3]));
+        const uint32_t nib = (Rw >> sh) & 15u;
+        const uint32_t rank = (w == 0 ? 0u : (w == 1 ? n0 : (w == 2 ? n1 : n2))) + __popc(Rw & ((1u << sh) - 1u));
+        const uint32_t cnt = __popc(nib);
+        const bool has0 = cnt >= 1, has1 = cnt >= 2;
+        // my (up to) two elements
+        const uint32_t pos0 = seg_lo + 4 * lane + (uint32_t)(__ffs((int)nib) - 1);
+        const uint32_t pos1 = seg_lo + 4 * lane + (uint32_t)(31 - __clz((int)nib));
+        const uint32_t v0 = ld_le32_any(in + (has0 ? pos0 : seg_lo), last_word);
+        const uint32_t v1 = ld_le32_any(in + (has1 ? pos1 : seg_lo), last_word);
+        const Header h0 = decode_header(v0, pos0), h1 = decode_header(v1, pos1);
+        const bool sp0 = has0 && (h0.slow || (h0.is_lit && h0.len >= kLongLiteral));
+        const bool sp1 = has1 && (h1.slow || (h1.is_lit && h1.len >= kLongLiteral));
+        // a 4-byte literal length does not fit v: take its top byte from the stream
+        uint32_t len0 = has0 ? h0.len : 0u, len1 = has1 ? h1.len : 0u;
+        if (has0 && h0.is_lit && h0.hdr == 5)
+            len0 = (((v0 >> 8) | ((pos0 + 4 < lim ? (uint32_t)__ldg(in + pos0 + 4) : 0u) << 24))) + 1u;
+        if (has1 && h1.is_lit && h1.hdr == 5)
+            len1 = (((v1 >> 8) | ((pos1 + 4 < lim ? (uint32_t)__ldg(in + pos1 + 4) : 0u) << 24))) + 1u;
+        // output offsets: 64-bit sums, so that absurd literal lengths cannot wrap around
+        uint64_t end = (uint64_t)len0 + len1;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                if (lastbit >= 32u * w + 31u)
-                    R[w] = 0;
-                else if (lastbit >= 32u * w)
-                    R[w] &= ~((2u << (lastbit - 32u * w)) - 1u);
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t u = __shfl_up_sync(kFull, end, d);
+            if ((int)lane >= d)
+                end += u;
+        }
+        const uint64_t T64 = __shfl_sync(kFull, end, 31);
+        const uint32_t start0 = (uint32_t)(end - len0 - len1), start1 = start0 + len0;
+        const bool corrupt0 = has0 && (pos0 + h0.hdr > lim || (h0.is_lit && (uint64_t)pos0 + h0.hdr + len0 > lim) ||
+                                       (!h0.is_lit && !h0.slow && h0.info == 0));
+        const bool corrupt1 = has1 && (pos1 + h1.hdr > lim || (h1.is_lit && (uint64_t)pos1 + h1.hdr + len1 > lim) ||
+                                       (!h1.is_lit && !h1.slow && h1.info == 0));
+        bool framing = (has0 && !h0.is_lit && !h0.slow && h0.info > op + start0) ||
+                       (has1 && !h1.is_lit && !h1.slow && h1.info > op + start1);
+        if (T64 > olen - op)
+            framing = true;
+        const unsigned BC = __ballot_sync(kFull, corrupt0 || corrupt1 || cnt > 2), BF = __ballot_sync(kFull, framing);
+        if (BC | BF) {
+            err = BC ? SNAPPY_B200_ST_CORRUPT : SNAPPY_B200_ST_FRAMING;
+            break;
+        }
+        const uint32_t T = (uint32_t)T64;
+        const unsigned S = __ballot_sync(kFull, sp0 || sp1);
+        // ---- the table
+        if (has0) {
+            uint32_t y = 0;
+            const uint8_t *p = in + h0.info - start0; // literal: byte k of the window = stream byte info + (k - start)
+            if (sp0) {
+                y = 0xffffffffu; // not for produce_run: z = stream position of the tag
+                p = reinterpret_cast<const uint8_t *>((uintptr_t)pos0);
+            } else if (!h0.is_lit) {
+                const uint32_t off = h0.info; // <= 65535 (copy-4 is special)
+                y = off | (off < len0 ? (32768u / off + 1u) << 16 : 0u);
+                p = out + op - off; // byte k of the window = output byte op + k - off
+            }
+            const uint64_t pa = reinterpret_cast<uint64_t>(p);
+            sm.elems[rank] = make_uint4(start0, y, (uint32_t)pa, (uint32_t)(pa >> 32));
+        }
+        if (has1) {
+            uint32_t y = 0;
+            const uint8_t *p = in + h1.info - start1;
+            if (sp1) {
+                y = 0xffffffffu;
+                p = reinterpret_cast<const uint8_t *>((uintptr_t)pos1);
+            } else if (!h1.is_lit) {
+                const uint32_t off = h1.info;
+                y = off | (off < len1 ? (32768u / off + 1u) << 16 : 0u);
+                p = out + op - off;
+            }
+            const uint64_t pa = reinterpret_cast<uint64_t>(p);
+            sm.elems[rank + 1] = make_uint4(start1, y, (uint32_t)pa, (uint32_t)(pa >> 32));
+        }
+        if (S == 0) {
+            // ---- the ordinary segment: one run
+            const uint32_t words = (T + 31) >> 5;
+            for (uint32_t i = lane; i < words; i += 32)
+                sm.bm[i] = 0;
+            __syncwarp();
+            if (has0)
+                atomicOr(&sm.bm[start0 >> 5], 1u << (start0 & 31u));
+            if (has1)
+                atomicOr(&sm.bm[start1 >> 5], 1u << (start1 & 31u));
+            __syncwarp(); // also: stores of earlier steps are visible to every lane from here
+            produce_run(out, op, 0, T, 0, sm, lane);
+        } else {
+            // ---- runs of ordinary elements between the special ones (long literals, copy-4, ...)
+            __syncwarp();
+            uint32_t e_lo = 0;
+            while (e_lo < ne && !err) {
+                // first special element at or after e_lo
+                uint32_t mine = 0xffffffffu;
+                if (sp0 && rank >= e_lo)
+                    mine = rank;
+                else if (sp1 && rank + 1 >= e_lo)
+                    mine = rank + 1;
+                const uint32_t e_sp = __reduce_min_sync(kFull, mine); // 0xffffffff: none
+                const uint32_t e_hi = min(e_sp, ne);
+                const uint32_t k_lo = sm.elems[e_lo].x;
+                const uint32_t k_hi = e_hi < ne ? sm.elems[e_hi].x : T;
+                if (e_hi > e_lo) {
+                    const uint32_t words = (k_hi - k_lo + 31) >> 5;
+                    for (uint32_t i = lane; i < words; i += 32)
+                        sm.bm[i] = 0;
+                    __syncwarp();
+                    if (has0 && rank >= e_lo && rank < e_hi)
+                        atomicOr(&sm.bm[(start0 - k_lo) >> 5], 1u << ((start0 - k_lo) & 31u));
+                    if (has1 && rank + 1 >= e_lo && rank + 1 < e_hi)
+                        atomicOr(&sm.bm[(start1 - k_lo) >> 5], 1u << ((start1 - k_lo) & 31u));
+                    __syncwarp();
+                    produce_run(out, op, k_lo, k_hi, e_lo, sm, lane);
+                }
+                if (e_hi < ne) {
+                    uint32_t ip = sm.elems[e_hi].z, o2 = op + k_hi;
+                    const uint32_t tv = ld_le32_any(in + ip, last_word);
+                    err = single_element(in, lim, tv, out, olen, blk, ip, o2, lane);
+                }
+                e_lo = e_hi + 1;
             }
         }
+        op += T;
     }
     if (!err && op != olen)
         err = SNAPPY_B200_ST_CORRUPT;
