@@ -268,3 +268,19 @@ def test_decoders_on_random_valid_streams(oracle):
         codec.index(d_stream, stream.size, hdr, total, got_offs)
         codec.check_status()
         assert np.array_equal(got_offs.cpu().numpy().astype(np.uint64), offs), f"K0 offsets {seed}"
+
+
+@pytest.mark.gpu
+def test_batch_tool_config4_small():
+    """BASELINE configs[4] at reduced size: tools/batch64.py (block-range sharding, sub-batches,
+    1 % oracle spot check, checksum) on a 256 MiB batch."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "batch64.py"), "--gib", "0.25", "--sub-gib", "0.125"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["roundtrip_ok"] and d["checksum_ok"] and d["oracle_checked_fraction"] >= 0.01
+    assert abs(d["ratio"] - 1.72) < 0.02
