@@ -364,6 +364,8 @@ int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *
     const uint8_t *src = static_cast<const uint8_t *>(in);
     uint8_t *dst = static_cast<uint8_t *>(out);
 
+    Trace trace;
+    trace.start(g_ctx.s_up);
     // Enqueues everything chunk j needs up to (and including) the read-back of its size.
     auto issue = [&](uint64_t j) -> cudaError_t {
         const int s = (int)(j % slots);
@@ -376,6 +378,7 @@ int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *
             e = cudaMemcpyAsync(g_ctx.buf[0 + s], src + lo, len, cudaMemcpyHostToDevice, g_ctx.s_up);
         if (e == cudaSuccess)
             e = cudaEventRecord(ev_up[s], g_ctx.s_up);
+        trace.mark("upload done, chunk " + std::to_string(j), g_ctx.s_up);
         if (e == cudaSuccess)
             e = cudaStreamWaitEvent(st, ev_up[s], 0);
         if (e == cudaSuccess && j >= (uint64_t)slots) // ... and its download has left the output buffer
@@ -390,6 +393,7 @@ int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *
                                g_ctx.buf[8 + s], st);
         if (e == cudaSuccess)
             e = cudaEventRecord(ev_run[s], st);
+        trace.mark("kernels done, chunk " + std::to_string(j), st);
         if (e == cudaSuccess)
             e = peek_u32(reinterpret_cast<uint32_t *>(g_ctx.h_small + 4 * s), d_bytes, 4, st);
         if (e == cudaSuccess)
@@ -416,9 +420,11 @@ int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *
         CU(cudaStreamWaitEvent(g_ctx.s_down, ev_run[s], 0), "stream wait");
         CU(cudaMemcpyAsync(dst + off, g_ctx.buf[4 + s], clen, cudaMemcpyDeviceToHost, g_ctx.s_down), "D2H copy");
         CU(cudaEventRecord(ev_down[s], g_ctx.s_down), "event record");
+        trace.mark("download done, chunk " + std::to_string(j) + " (" + std::to_string(clen >> 20) + " MiB)", g_ctx.s_down);
         off += clen;
     }
     CU(cudaStreamSynchronize(g_ctx.s_down), "D2H copy");
+    trace.dump();
     *out_bytes = off;
     return SNAPPY_B200_OK;
 }
