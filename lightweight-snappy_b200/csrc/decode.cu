@@ -235,7 +235,46 @@ __device__ __forceinline__ uint32_t run_step(const uint8_t *__restrict__ in, uin
 constexpr uint32_t kSegElems = 64;
 constexpr uint32_t kRunBytes = kSegElems * 64; // output bytes of a run of ordinary elements (each <= 64)
 
+// Tag byte -> header facts, looked up instead of branched over (two headers per lane per step):
+//   bits 0-2 header bytes, bits 3-9 output length when the tag alone gives it (0: a literal whose
+//   length follows in 1..4 bytes), bit 10 literal, bit 11 needs the one-element path whatever its
+//   length (copy-4, 4-byte literal length), bit 12 copy with a 1-byte offset.
+constexpr uint32_t kTagLit = 1u << 10, kTagSlow = 1u << 11, kTagCopy1 = 1u << 12;
+
+__device__ __forceinline__ uint32_t tag_facts(uint32_t tag)
+{
+    const uint32_t type = tag & 3u, m = tag >> 2;
+    if (type == 0) {
+        if (m < 60)
+            return 1u | ((m + 1u) << 3) | kTagLit;
+        const uint32_t k = m - 59u; // length bytes
+        return (1u + k) | kTagLit | (k == 4 ? kTagSlow : 0u);
+    }
+    if (type == 1)
+        return 2u | (((m & 7u) + 4u) << 3) | kTagCopy1;
+    if (type == 2)
+        return 3u | ((m + 1u) << 3);
+    return 5u | ((m + 1u) << 3) | kTagSlow;
+}
+
+// The same element facts as decode_header() from the table (v = the 4 stream bytes at pos).
+__device__ __forceinline__ Header decode_header_lut(const uint16_t *__restrict__ lut, uint32_t v, uint32_t pos)
+{
+    Header h;
+    const uint32_t f = lut[v & 0xffu];
+    h.hdr = f & 7u;
+    h.len = (f >> 3) & 127u;
+    h.is_lit = f & kTagLit;
+    h.slow = f & kTagSlow;
+    if (h.len == 0) // literal with 1..4 length bytes (the fourth one does not fit v: the caller's business)
+        h.len = ((v >> 8) & (0xffffffu >> (8u * (4u - min(h.hdr, 4u))))) + 1u;
+    const uint32_t c1 = ((v << 3) & 0x700u) | ((v >> 8) & 0xffu), c2 = (v >> 8) & 0xffffu;
+    h.info = h.is_lit ? pos + h.hdr : ((f & kTagCopy1) ? c1 : c2);
+    return h;
+}
+
 struct SegSmem {
+    uint16_t lut[256];
     uint4 elems[kSegElems];
     uint32_t bm[kRunBytes / 32 + 4]; // element starts inside the current run, one bit per output byte
 };
@@ -312,6 +351,9 @@ __global__ void __launch_bounds__(32) k_decode_seg(const uint8_t *__restrict__ s
     const uint64_t oleft = total_out - blk * (uint64_t)kBlock;
     const uint32_t olen = oleft < kBlock ? (uint32_t)oleft : kBlock;
     const uint32_t w = lane >> 3, sh = (lane & 7u) * 4u; // my nibble of the 128-bit start map
+    for (uint32_t i = lane; i < 256; i += 32)
+        sm.lut[i] = (uint16_t)tag_facts(i);
+    __syncwarp();
 
     uint32_t op = 0, err = 0;
     for (uint64_t t = t0; t <= t1 && !err; ++t) {
@@ -345,7 +387,7 @@ __global__ void __launch_bounds__(32) k_decode_seg(const uint8_t *__restrict__ s
         const uint32_t pos1 = seg_lo + 4 * lane + (uint32_t)(31 - __clz((int)nib));
         const uint32_t v0 = ld_le32_any(in + (has0 ? pos0 : seg_lo), last_word);
         const uint32_t v1 = ld_le32_any(in + (has1 ? pos1 : seg_lo), last_word);
-        const Header h0 = decode_header(v0, pos0), h1 = decode_header(v1, pos1);
+        const Header h0 = decode_header_lut(sm.lut, v0, pos0), h1 = decode_header_lut(sm.lut, v1, pos1);
         const bool sp0 = has0 && (h0.slow || (h0.is_lit && h0.len >= kLongLiteral));
         const bool sp1 = has1 && (h1.slow || (h1.is_lit && h1.len >= kLongLiteral));
         // a 4-byte literal length does not fit v: take its top byte from the stream
