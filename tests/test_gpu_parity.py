@@ -284,3 +284,14 @@ def test_batch_tool_config4_small():
     d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert d["roundtrip_ok"] and d["checksum_ok"] and d["oracle_checked_fraction"] >= 0.01
     assert abs(d["ratio"] - 1.72) < 0.02
+
+
+@pytest.mark.gpu
+def test_selftest_driver():
+    """the snappy_test-shaped round-trip driver over generated fixtures (the six
+    named files + 13 sizes x 5), both compressors, through the FILE*-based drop-in API."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "lightweight-snappy_b200", "snappy_b200_test")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-1000:])
+    assert "142 round trips, 0 failed" in r.stdout
