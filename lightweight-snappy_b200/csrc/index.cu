@@ -448,6 +448,73 @@ __global__ void __launch_bounds__(kGroupCta) k_group_apply(const uint8_t *__rest
     }
 }
 
+// The same step with one LANE per group for the part every group goes through (two loads and,
+// for nearly all groups after the first round, the finding that nothing changed); the few groups
+// whose new entry is off their known chain are then re-resolved one after the other by the
+// whole warp.  Lane l of warp w takes group l * n_warps + w, so that neighbouring groups -- which
+// tend to need work together -- land in different warps.  32x fewer warps than k_group_apply.
+__global__ void __launch_bounds__(kGroupCta) k_group_apply32(const uint8_t *__restrict__ body, uint64_t body_len,
+                                                             uint64_t nseg, uint64_t ngroup, uint4 *__restrict__ paths,
+                                                             uint64_t *__restrict__ exits,
+                                                             uint32_t *__restrict__ g_entry,
+                                                             uint64_t *__restrict__ g_exit,
+                                                             uint64_t *__restrict__ g_vis,
+                                                             unsigned long long *__restrict__ g_claim,
+                                                             uint32_t *__restrict__ changed)
+{
+    __shared__ GroupStage stage[kGroupCta / 32];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n_warps = (uint64_t)gridDim.x * (kGroupCta / 32);
+    const uint64_t w = blockIdx.x * (uint64_t)(kGroupCta / 32) + (threadIdx.x >> 5);
+    const uint64_t g = lane * n_warps + w;
+    bool moved = false, heavy = false;
+    uint64_t e = 0;
+    if (g < ngroup) {
+        const unsigned long long c = g_claim[g];
+        const uint32_t old = g_entry[g];
+        g_claim[g] = kNone; // ready for the next round
+        const uint32_t payload = (uint32_t)(c & 0xffffffu);
+        uint32_t ne;
+        if (g == 0)
+            ne = 0; // the body starts with an element
+        else if (c == kNone || payload == kGMark)
+            ne = (old & ~kGDead) | kGDead;
+        else
+            ne = payload;
+        if (ne != old) {
+            moved = true;
+            g_entry[g] = ne;
+            if (!(ne & kGDead) && ne != (old & ~kGDead)) { // (else: dead, or revived with the entry it already chased from)
+                e = g * kGroupBytes + ne; // does the new entry lie on the old chain?
+                const uint64_t sg = e / kSeg;
+                const uint4 pv = paths[sg];
+                Path p;
+                p.bits[0] = pv.x, p.bits[1] = pv.y, p.bits[2] = pv.z, p.bits[3] = pv.w;
+                heavy = !(((g_vis[g] >> (sg - g * kGroup)) & 1ull) && p.test((uint32_t)(e - sg * kSeg)));
+            }
+        }
+    }
+    if (__any_sync(kFull, moved) && lane == 0)
+        atomicOr(changed, 1u);
+    unsigned H = __ballot_sync(kFull, heavy);
+    GroupStage &sm = stage[threadIdx.x >> 5];
+    while (H) {
+        const int src = __ffs((int)H) - 1;
+        H &= H - 1;
+        const uint64_t gg = (uint64_t)src * n_warps + w;
+        const uint64_t ee = __shfl_sync(kFull, e, src);
+        group_stage(sm, gg, nseg, paths, exits);
+        uint64_t vis;
+        const uint64_t x = group_resolve(body, body_len, nseg, sm, gg, ee, vis);
+        group_unstage(sm, gg, nseg, paths, exits);
+        if (lane == 0) {
+            g_exit[gg] = x;
+            g_vis[gg] = vis;
+        }
+        __syncwarp();
+    }
+}
+
 // Last pass over the tags.  Every live group chases once more from its true entry, which gives
 // the entry of each of its segments; every live segment is then walked from that entry (C): the
 // output bytes of the elements that start in it are summed, and the (speculative) path map is
@@ -785,6 +852,7 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
     const uint64_t ngroup = (nseg + kGroup - 1) / kGroup;
     const unsigned ggrid = (unsigned)((ngroup + 127) / 128);                       // one thread per group
     const unsigned wgrid = (unsigned)((ngroup + kGroupCta / 32 - 1) / (kGroupCta / 32)); // one warp per group
+    const unsigned wgrid32 = (unsigned)((ngroup + kGroupCta - 1) / kGroupCta);           // one lane per group
     k_index_spec<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits);
     k_group_init<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.g_exit, w.g_vis,
                                         w.claim);
@@ -799,8 +867,12 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
     for (uint64_t round = 0; round < max_rounds; round += batch, batch = min(batch * 2, kMaxBatch)) {
         for (uint32_t k = 0; k < batch; ++k) {
             k_group_scatter<<<ggrid, 128, 0, st>>>(body, body_len, ngroup, w.g_entry, w.g_exit, w.claim);
-            k_group_apply<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry,
-                                                       w.g_exit, w.g_vis, w.claim, w.changed + k);
+            if (round + k == 0) // the first round moves most groups: one warp each
+                k_group_apply<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry,
+                                                           w.g_exit, w.g_vis, w.claim, w.changed + k);
+            else
+                k_group_apply32<<<wgrid32, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits,
+                                                               w.g_entry, w.g_exit, w.g_vis, w.claim, w.changed + k);
         }
         *launches += 2 * batch;
         uint32_t *changed = thread_pinned_scratch(); // >= kMaxBatch words
