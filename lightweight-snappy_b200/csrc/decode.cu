@@ -3,8 +3,8 @@
 // reference: decompressor src/snappy_decompression.c:290-333 (tag dispatch), do_literal
 // :193-224, write_literal :232-239, do_copy :253-265, write_copy :273-280.
 //
-// The reference walks one element at a time.  Both kernels here decode up to 32 elements per
-// step, one per lane, and then produce the output bytes of all of them 32 at a time:
+// The reference walks one element at a time.  Both kernels here decode many elements per step
+// and then produce the output bytes of all of them 32 at a time:
 //   * a warp prefix sum of the output lengths gives every element its output offset;
 //   * the elements go into a small shared-memory table; in every round the lane that produces
 //     output byte k finds its element from a bit map of the element starts inside the round
@@ -21,7 +21,9 @@
 //
 // What differs is how a step finds its elements:
 //   k_decode_seg   (index-less streams, after K0) takes them from the exact element-start bit
-//                  maps K0 leaves per 128-byte stream segment: lane r gets the r-th start.
+//                  maps K0 leaves per 128-byte stream segment.  A step is one segment: lane l
+//                  owns the (at most two) elements that start in stream bytes 4l..4l+3, their
+//                  rank is a popcount of the map below, headers come from a tag table.
 //   k_decode_warp  (caller supplied block index, no K0) looks at a 32-byte window: every lane
 //                  decodes the byte at its offset as if an element started there, and the
 //                  real starts are the orbit of lane 0 under "next = lane + element size",
