@@ -37,6 +37,9 @@
 // tags (write_literal :95-120, write_copy :153-165, write_single_copy :131-145) are sized,
 // prefix-summed and written in parallel into the block's scratch slot; long literals are
 // copied by the whole CTA with 16-byte stores.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sb200 {
@@ -76,7 +79,10 @@ __device__ __forceinline__ uint32_t match_extend(const uint8_t *__restrict__ b, 
 }
 
 // ------------------------------------------------------------------------------- exact table
-template <int LOG_SLOTS> struct ExactTable {
+// GLOBAL: the table lives in global memory (the big tier, see launch_compress).  It is private to
+// one warp, but lanes insert with atomics, which are performed in L2: the reads then go to L2 as
+// well (__ldcg) instead of trusting a line in L1.
+template <int LOG_SLOTS, bool GLOBAL = false> struct ExactTable {
     static constexpr uint32_t kSlots = 1u << LOG_SLOTS;
     static constexpr uint32_t kEmpty = 0xffffu;
     uint16_t *tab;
@@ -89,7 +95,7 @@ template <int LOG_SLOTS> struct ExactTable {
     {
         uint32_t s = home(key);
         for (;;) {
-            const uint32_t v = tab[s];
+            const uint32_t v = GLOBAL ? __ldcg(tab + s) : tab[s];
             if (v == kEmpty) {
                 found = false;
                 pos = 0;
@@ -122,15 +128,12 @@ template <int LOG_SLOTS> struct ExactTable {
 // MODE 0 = hash table (LOG_SLOTS ignored: the table has up to 4096 u32 entries)
 // MODE 1 = exact dictionary with 2^LOG_SLOTS u16 slots; a block whose dictionary would grow
 //          past 3/4 of the table gives up (nrec[blk] = kAbortMark) unless FINAL.
-template <int MODE, int LOG_SLOTS, bool FINAL>
-__global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, uint64_t n_bytes,
-                                              uint2 *__restrict__ recs, uint32_t *__restrict__ nrec, int only_marked)
+// smem_raw: the table memory (shared, or global when GLOBAL).
+template <int MODE, int LOG_SLOTS, bool FINAL, bool GLOBAL = false>
+__device__ __forceinline__ void parse_block(const uint8_t *__restrict__ in, uint64_t n_bytes, uint2 *__restrict__ recs,
+                                            uint32_t *__restrict__ nrec, uint64_t blk, uint8_t *smem_raw)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = threadIdx.x;
-    const uint64_t blk = blockIdx.x;
-    if (only_marked && nrec[blk] != kAbortMark)
-        return;
 
     const uint8_t *__restrict__ b = in + blk * (uint64_t)kBlock;
     const uint64_t left = n_bytes - blk * (uint64_t)kBlock;
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
 
     uint16_t *hpos = reinterpret_cast<uint16_t *>(smem_raw);   // hash mode: candidate position per slot
     uint8_t *hfp = smem_raw + 2 * SNAPPY_B200_HTABLE_SIZE;     // hash mode: key fingerprint per slot
-    ExactTable<LOG_SLOTS> et{reinterpret_cast<uint16_t *>(smem_raw)};
+    ExactTable<LOG_SLOTS, GLOBAL> et{reinterpret_cast<uint16_t *>(smem_raw)};
     uint32_t shift = 20;
     uint32_t n_keys = 0; // exact mode: dictionary population (warp-uniform)
 
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
     } else {
         uint4 *t4 = reinterpret_cast<uint4 *>(smem_raw);
         const uint4 init = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        for (uint32_t i = lane; i < ExactTable<LOG_SLOTS>::kSlots / 8; i += 32)
+        for (uint32_t i = lane; i < ExactTable<LOG_SLOTS, GLOBAL>::kSlots / 8; i += 32)
             t4[i] = init;
     }
     __syncwarp();
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
             __syncwarp();
         }
 
-        if (MODE == 1 && !FINAL && n_keys > (ExactTable<LOG_SLOTS>::kSlots * 3) / 4) {
+        if (MODE == 1 && !FINAL && n_keys > (ExactTable<LOG_SLOTS, GLOBAL>::kSlots * 3) / 4) {
             if (lane == 0)
                 nrec[blk] = kAbortMark;
             return;
@@ -498,6 +501,43 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
         my_recs[(nh & ~31u) + lane] = rec;
     if (lane == 0)
         nrec[blk] = nh;
+}
+
+template <int MODE, int LOG_SLOTS, bool FINAL>
+__global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, uint64_t n_bytes,
+                                              uint2 *__restrict__ recs, uint32_t *__restrict__ nrec, int only_marked)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint64_t blk = blockIdx.x;
+    if (only_marked && nrec[blk] != kAbortMark)
+        return;
+    parse_block<MODE, LOG_SLOTS, FINAL>(in, n_bytes, recs, nrec, blk, smem_raw);
+}
+
+// The big exact tier: 2^16 slots (128 KiB) per chain do not fit many times into shared memory
+// (1 chain per SM), and a chain is bound by latency, not by bandwidth -- so the tables go to global
+// memory (the blocks' output slots, which nothing uses before k_emit) and every SM runs as many
+// chains as it can hold warps for.  Persistent CTAs: each owns one table and takes marked blocks
+// from a counter.
+constexpr int kGlobalTierLog = 16;
+__global__ void __launch_bounds__(32) k_parse_exact_global(const uint8_t *__restrict__ in, uint64_t n_bytes,
+                                                           uint64_t n_blocks, uint2 *__restrict__ recs,
+                                                           uint32_t *__restrict__ nrec, uint8_t *__restrict__ tables,
+                                                           uint32_t *__restrict__ counter)
+{
+    uint8_t *table = tables + (size_t)blockIdx.x * ((size_t)2 << kGlobalTierLog);
+    for (;;) {
+        uint32_t blk = 0;
+        if (threadIdx.x == 0)
+            blk = atomicAdd(counter, 1u);
+        blk = __shfl_sync(kFull, blk, 0);
+        if (blk >= n_blocks)
+            return;
+        if (nrec[blk] != kAbortMark)
+            continue;
+        parse_block<1, kGlobalTierLog, true, true>(in, n_bytes, recs, nrec, blk, table);
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------------------- emission
@@ -694,9 +734,24 @@ cudaError_t launch_compress(const uint8_t *d_in, uint64_t n_bytes, int mode, uin
             attr_done = true;
         }
         k_parse<1, 13, false><<<grid, cta, (1 << 13) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 0);
-        k_parse<1, 15, false><<<grid, cta, (1 << 15) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 1);
-        k_parse<1, 16, true><<<grid, cta, (1 << 16) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 1);
-        *launches += 3;
+        // blocks with more than 6144 distinct keys: tables in global memory, carved out of the output
+        // slots (free until k_emit), as many chains as the SMs hold warps for
+        const uint64_t table_bytes = (uint64_t)2 << kGlobalTierLog;
+        static int n_sm = 0;
+        if (!n_sm && cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess)
+            n_sm = 148;
+        const uint64_t n_tables = std::min<uint64_t>(nb * (uint64_t)kSlot / table_bytes, (uint64_t)n_sm * 32);
+        if (n_tables >= 1 && !getenv("SNAPPY_B200_BST_SMEM_TIERS")) {
+            cudaError_t e = cudaMemsetAsync(d_sizes, 0, 4, st); // the work counter (k_emit overwrites sizes later)
+            if (e != cudaSuccess)
+                return e;
+            k_parse_exact_global<<<(unsigned)n_tables, cta, 0, st>>>(d_in, n_bytes, nb, d_recs, d_nrec, d_scratch, d_sizes);
+            *launches += 2;
+        } else {
+            k_parse<1, 15, false><<<grid, cta, (1 << 15) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 1);
+            k_parse<1, 16, true><<<grid, cta, (1 << 16) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 1);
+            *launches += 3;
+        }
     }
     k_emit<<<grid, kEmitThreads, 0, st>>>(d_in, n_bytes, d_recs, d_nrec, d_scratch, d_sizes);
     *launches += 1;
