@@ -133,7 +133,7 @@ template <int MODE, int LOG_SLOTS, bool FINAL, bool GLOBAL = false>
 __device__ __forceinline__ void parse_block(const uint8_t *__restrict__ in, uint64_t n_bytes, uint2 *__restrict__ recs,
                                             uint32_t *__restrict__ nrec, uint64_t blk, uint8_t *smem_raw)
 {
-    const uint32_t lane = threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
 
     const uint8_t *__restrict__ b = in + blk * (uint64_t)kBlock;
     const uint64_t left = n_bytes - blk * (uint64_t)kBlock;
@@ -217,8 +217,8 @@ __device__ __forceinline__ void parse_block(const uint8_t *__restrict__ in, uint
                 if (hfp[idx] == ph) {
                     const uint32_t *cw = reinterpret_cast<const uint32_t *>(b) + (cand >> 2);
                     const uint32_t sh = (cand & 3u) * 8u;
-                    const uint32_t w0 = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2), w3 = __ldg(cw + 3),
-                                   w4 = __ldg(cw + 4);
+                    const uint32_t w0 = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2),
+                                   w3 = __ldg(cw + 3), w4 = __ldg(cw + 4);
                     hit = __funnelshift_r(w0, w1, sh) == __funnelshift_r(k0, k1, psh);
                     const uint32_t x1 = __funnelshift_r(w1, w2, sh) ^ __funnelshift_r(k1, k2, psh);
                     const uint32_t x2 = __funnelshift_r(w2, w3, sh) ^ __funnelshift_r(k2, k3, psh);
@@ -520,12 +520,13 @@ __global__ void __launch_bounds__(32) k_parse(const uint8_t *__restrict__ in, ui
 // chains as it can hold warps for.  Persistent CTAs: each owns one table and takes marked blocks
 // from a counter.
 constexpr int kGlobalTierLog = 16;
+template <int LOG_SLOTS, bool FINAL>
 __global__ void __launch_bounds__(32) k_parse_exact_global(const uint8_t *__restrict__ in, uint64_t n_bytes,
                                                            uint64_t n_blocks, uint2 *__restrict__ recs,
                                                            uint32_t *__restrict__ nrec, uint8_t *__restrict__ tables,
-                                                           uint32_t *__restrict__ counter)
+                                                           uint32_t *__restrict__ counter, int only_marked)
 {
-    uint8_t *table = tables + (size_t)blockIdx.x * ((size_t)2 << kGlobalTierLog);
+    uint8_t *table = tables + (size_t)blockIdx.x * ((size_t)2 << LOG_SLOTS);
     for (;;) {
         uint32_t blk = 0;
         if (threadIdx.x == 0)
@@ -533,9 +534,32 @@ __global__ void __launch_bounds__(32) k_parse_exact_global(const uint8_t *__rest
         blk = __shfl_sync(kFull, blk, 0);
         if (blk >= n_blocks)
             return;
-        if (nrec[blk] != kAbortMark)
+        if (only_marked && nrec[blk] != kAbortMark)
             continue;
-        parse_block<1, kGlobalTierLog, true, true>(in, n_bytes, recs, nrec, blk, table);
+        parse_block<1, LOG_SLOTS, FINAL, true>(in, n_bytes, recs, nrec, blk, table);
+        __syncwarp();
+    }
+}
+
+// Hash mode with the two table arrays (12 KiB per chain) in global memory: persistent one-warp CTAs,
+// 32 per SM, each with its own tables, taking blocks from a counter.  With nothing in shared
+// memory the SM's whole 256 KB is L1, which keeps the hot part of the tables close, and 32
+// latency-bound chains per SM beat the 17-18 that 12 KiB shared-memory tables allow (measured:
+// 16.0 -> 14.0 ms per GiB of the mixed corpus; the k_parse<0> kernel is the shared-memory version).
+__global__ void __launch_bounds__(32) k_parse_hash_global(const uint8_t *__restrict__ in, uint64_t n_bytes,
+                                                          uint64_t n_blocks, uint2 *__restrict__ recs,
+                                                          uint32_t *__restrict__ nrec, uint8_t *__restrict__ tables,
+                                                          uint32_t *__restrict__ counter)
+{
+    uint8_t *table = tables + (size_t)blockIdx.x * (size_t)(3 * SNAPPY_B200_HTABLE_SIZE);
+    for (;;) {
+        uint32_t blk = 0;
+        if (threadIdx.x == 0)
+            blk = atomicAdd(counter, 1u);
+        blk = __shfl_sync(kFull, blk, 0);
+        if (blk >= n_blocks)
+            return;
+        parse_block<0, 12, true, true>(in, n_bytes, recs, nrec, blk, table);
         __syncwarp();
     }
 }
@@ -717,15 +741,30 @@ cudaError_t launch_compress(const uint8_t *d_in, uint64_t n_bytes, int mode, uin
     if (nb > 0x7fffffffull)
         return cudaErrorInvalidValue;
     const dim3 grid((unsigned)nb), cta(32);
+    // Tables in global memory: carved out of the blocks' output slots, which nothing uses before
+    // k_emit; the last 256 bytes of that area hold the work counters of the persistent kernels.
+    static int n_sm = 0;
+    if (!n_sm && cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess)
+        n_sm = 148;
+    const uint64_t chains = std::min<uint64_t>(nb, (uint64_t)n_sm * 32); // one-warp CTAs: 32 per SM
+    const uint64_t area = nb * (uint64_t)kSlot - 256;
+    uint32_t *counters = reinterpret_cast<uint32_t *>(d_scratch + area);
+    const bool smem_tables = getenv("SNAPPY_B200_SMEM_TABLES") != nullptr; // the measured alternative
+    cudaError_t e = smem_tables ? cudaSuccess : cudaMemsetAsync(counters, 0, 16, st);
+    if (e != cudaSuccess)
+        return e;
     if (mode == SNAPPY_B200_MODE_HASH) {
-        k_parse<0, 12, true><<<grid, cta, 4096 * 3, st>>>(d_in, n_bytes, d_recs, d_nrec, 0);
+        if (smem_tables)
+            k_parse<0, 12, true><<<grid, cta, 4096 * 3, st>>>(d_in, n_bytes, d_recs, d_nrec, 0);
+        else
+            k_parse_hash_global<<<(unsigned)chains, cta, 0, st>>>(d_in, n_bytes, nb, d_recs, d_nrec, d_scratch, counters);
         *launches += 1;
     } else {
-        // exact mode: 8 Ki slots (16 KiB), then 32 Ki slots (64 KiB), then 64 Ki slots (128 KiB)
+        // exact mode: 8 Ki slots (16 KiB), then 64 Ki slots (128 KiB) for the blocks that outgrow them
+        // (> 6144 distinct keys: text)
         static bool attr_done = false;
         if (!attr_done) {
-            cudaError_t e = cudaFuncSetAttribute(k_parse<1, 15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (1 << 15) * 2);
+            e = cudaFuncSetAttribute(k_parse<1, 15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 15) * 2);
             if (e != cudaSuccess)
                 return e;
             e = cudaFuncSetAttribute(k_parse<1, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 16) * 2);
@@ -733,21 +772,17 @@ cudaError_t launch_compress(const uint8_t *d_in, uint64_t n_bytes, int mode, uin
                 return e;
             attr_done = true;
         }
-        k_parse<1, 13, false><<<grid, cta, (1 << 13) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 0);
-        // blocks with more than 6144 distinct keys: tables in global memory, carved out of the output
-        // slots (free until k_emit), as many chains as the SMs hold warps for
-        const uint64_t table_bytes = (uint64_t)2 << kGlobalTierLog;
-        static int n_sm = 0;
-        if (!n_sm && cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess)
-            n_sm = 148;
-        const uint64_t n_tables = std::min<uint64_t>(nb * (uint64_t)kSlot / table_bytes, (uint64_t)n_sm * 32);
-        if (n_tables >= 1 && !getenv("SNAPPY_B200_BST_SMEM_TIERS")) {
-            cudaError_t e = cudaMemsetAsync(d_sizes, 0, 4, st); // the work counter (k_emit overwrites sizes later)
-            if (e != cudaSuccess)
-                return e;
-            k_parse_exact_global<<<(unsigned)n_tables, cta, 0, st>>>(d_in, n_bytes, nb, d_recs, d_nrec, d_scratch, d_sizes);
+        if (smem_tables)
+            k_parse<1, 13, false><<<grid, cta, (1 << 13) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 0);
+        else
+            k_parse_exact_global<13, false><<<(unsigned)chains, cta, 0, st>>>(d_in, n_bytes, nb, d_recs, d_nrec,
+                                                                              d_scratch, counters + 1, 0);
+        const uint64_t n_big = std::min<uint64_t>(area / ((uint64_t)2 << kGlobalTierLog), chains);
+        if (n_big >= 1 && !smem_tables) {
+            k_parse_exact_global<kGlobalTierLog, true><<<(unsigned)n_big, cta, 0, st>>>(d_in, n_bytes, nb, d_recs, d_nrec,
+                                                                                     d_scratch, counters + 2, 1);
             *launches += 2;
-        } else {
+        } else { // a single block (or the A/B switch): the big tiers in shared memory
             k_parse<1, 15, false><<<grid, cta, (1 << 15) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 1);
             k_parse<1, 16, true><<<grid, cta, (1 << 16) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 1);
             *launches += 3;
