@@ -284,7 +284,7 @@ def run_gpu_arm(args) -> None:
     codec.check_status()
     td["kernel_ms"] = tk["kernel_ms"]
     td["unpipelined_ms_per_step"] = tk["total_ms"] / args.steps
-    tc = timed(step_compress, "k_parse<hash> (+ k_emit + k_scan_sizes + k_gather)")
+    tc = timed(step_compress, "k_parse_hash_global (+ k_emit + k_scan_sizes + k_gather)")
     codec.check_status()
 
     # ---- end to end through the host-buffer C-ABI (pinned host memory, copies inside)
