@@ -131,7 +131,8 @@ template <int LOG_SLOTS, bool GLOBAL = false> struct ExactTable {
 // smem_raw: the table memory (shared, or global when GLOBAL).
 template <int MODE, int LOG_SLOTS, bool FINAL, bool GLOBAL = false>
 __device__ __forceinline__ void parse_block(const uint8_t *__restrict__ in, uint64_t n_bytes, uint2 *__restrict__ recs,
-                                            uint32_t *__restrict__ nrec, uint64_t blk, uint8_t *smem_raw)
+                                            uint32_t *__restrict__ nrec, uint64_t blk, uint8_t *smem_raw,
+                                            uint8_t *fp_mem = nullptr)
 {
     const uint32_t lane = threadIdx.x & 31u;
 
@@ -148,7 +149,7 @@ __device__ __forceinline__ void parse_block(const uint8_t *__restrict__ in, uint
     constexpr uint32_t D = MODE == 0 ? 0 : 1;
 
     uint16_t *hpos = reinterpret_cast<uint16_t *>(smem_raw);   // hash mode: candidate position per slot
-    uint8_t *hfp = smem_raw + 2 * SNAPPY_B200_HTABLE_SIZE;     // hash mode: key fingerprint per slot
+    uint8_t *hfp = fp_mem ? fp_mem : smem_raw + 2 * SNAPPY_B200_HTABLE_SIZE; // hash mode: key fingerprint per slot
     ExactTable<LOG_SLOTS, GLOBAL> et{reinterpret_cast<uint16_t *>(smem_raw)};
     uint32_t shift = 20;
     uint32_t n_keys = 0; // exact mode: dictionary population (warp-uniform)
@@ -211,10 +212,11 @@ __device__ __forceinline__ void parse_block(const uint8_t *__restrict__ in, uint
                 const uint32_t prod = key * kHashMul;
                 const uint32_t idx = prod >> shift;
                 const uint32_t ph = (prod >> 12) & 0xffu;
-                const uint32_t cand = hpos[idx];
+                uint32_t cand = 0;
                 bool hit = false;
                 uint32_t ext = 0;
                 if (hfp[idx] == ph) {
+                    cand = hpos[idx];
                     const uint32_t *cw = reinterpret_cast<const uint32_t *>(b) + (cand >> 2);
                     const uint32_t sh = (cand & 3u) * 8u;
                     const uint32_t w0 = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2),
@@ -261,12 +263,13 @@ __device__ __forceinline__ void parse_block(const uint8_t *__restrict__ in, uint
             const uint32_t nk1 = __shfl_down_sync(kFull, key, 8);
             const uint32_t nk2 = __shfl_down_sync(kFull, key, 16);
             const uint32_t nk3 = __shfl_down_sync(kFull, key, 24);
-            const uint32_t tpos = hpos[idx];
             const uint32_t tfp = hfp[idx];
             // found_match :259-265 and a head start on find_copy_length :61-72: probes whose
             // fingerprint agrees fetch the candidate's bytes now, so that the round trip overlaps
-            // the in-step forwarding below (tpos + 19 < pos + 19 < n: all five words are inside)
+            // the in-step forwarding below (tpos + 19 < pos + 19 < n: all five words are inside).
+            // Only they read the position (the fingerprints are the array that is kept closest).
             const bool want = odd && tfp == ph;
+            const uint32_t tpos = want ? hpos[idx] : 0u;
             const uint32_t *cw = reinterpret_cast<const uint32_t *>(b) + (tpos >> 2);
             uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;
             if (want) {
@@ -552,6 +555,7 @@ __global__ void __launch_bounds__(32) k_parse_hash_global(const uint8_t *__restr
                                                           uint32_t *__restrict__ counter)
 {
     uint8_t *table = tables + (size_t)blockIdx.x * (size_t)(3 * SNAPPY_B200_HTABLE_SIZE);
+    __shared__ __align__(16) uint8_t fp_smem[SNAPPY_B200_HTABLE_SIZE];
     for (;;) {
         uint32_t blk = 0;
         if (threadIdx.x == 0)
@@ -559,7 +563,7 @@ __global__ void __launch_bounds__(32) k_parse_hash_global(const uint8_t *__restr
         blk = __shfl_sync(kFull, blk, 0);
         if (blk >= n_blocks)
             return;
-        parse_block<0, 12, true, true>(in, n_bytes, recs, nrec, blk, table);
+        parse_block<0, 12, true, true>(in, n_bytes, recs, nrec, blk, table, fp_smem);
         __syncwarp();
     }
 }
@@ -743,8 +747,9 @@ cudaError_t launch_compress(const uint8_t *d_in, uint64_t n_bytes, int mode, uin
     const dim3 grid((unsigned)nb), cta(32);
     // Tables in global memory: carved out of the blocks' output slots, which nothing uses before
     // k_emit; the last 256 bytes of that area hold the work counters of the persistent kernels.
-    static int n_sm = 0;
-    if (!n_sm && cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess)
+    int n_sm = 0, dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n_sm <= 0)
         n_sm = 148;
     const uint64_t chains = std::min<uint64_t>(nb, (uint64_t)n_sm * 32); // one-warp CTAs: 32 per SM
     const uint64_t area = nb * (uint64_t)kSlot - 256;
