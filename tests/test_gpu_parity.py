@@ -295,3 +295,15 @@ def test_selftest_driver():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-1000:])
     assert "142 round trips, 0 failed" in r.stdout
+
+
+@pytest.mark.gpu
+def test_shared_memory_table_variant(oracle, monkeypatch):
+    """The A/B switch SNAPPY_B200_SMEM_TABLES=1 (tables in shared memory, one CTA per block: the
+    kernels the global-memory tables replaced) must give the same bytes."""
+    monkeypatch.setenv("SNAPPY_B200_SMEM_TABLES", "1")
+    specs = _fuzz_specs()[::7] + ["corpus:text:3:0:300000", "corpus:lowent:3:0:300000", "corpus:mixed:3:0:3200000"]
+    for spec in specs:
+        data = datasets.gen(spec)
+        for mode, fn in ((0, api.snappy_compress), (1, api.snappy_compress_bst)):
+            _assert_same(fn(data), oracle.compress(data, mode), f"{spec} mode {mode} (shared-memory tables)")
