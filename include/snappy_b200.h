@@ -33,6 +33,7 @@
 #define SNAPPY_B200_H
 
 #include <stddef.h>
+#include <stdio.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -133,6 +134,22 @@ int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *
 int snappy_b200_uncompressed_length(const void *stream, uint64_t stream_bytes, uint64_t *n_bytes);
 int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void *out, uint64_t out_capacity,
                                 uint64_t *out_bytes);
+/* The same two calls with the optional side index: block_offsets[b] is the
+ * stream offset at which the b-th 64 KiB block starts, block_offsets[snappy_b200_block_count(n)]
+ * the stream length.  The stream itself is unchanged (byte-identical to the reference); a decoder
+ * that is handed the index does not have to discover the block boundaries (no K0).  The
+ * indexed decoder checks the index against the stream and reports SNAPPY_B200_ERR_CORRUPT /
+ * _FRAMING when they disagree.                                                            */
+int snappy_b200_compress_host_indexed(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
+                                      uint64_t *out_bytes, uint64_t *block_offsets);
+int snappy_b200_decompress_host_indexed(const void *stream, uint64_t stream_bytes, const uint64_t *block_offsets,
+                                        uint64_t n_blocks, void *out, uint64_t out_capacity, uint64_t *out_bytes);
+/* FILE*-level versions for the command line (`snappy -i`): the index is written to / read from its
+ * own file next to the unchanged stream -- "SNPIDX1\0", u64 uncompressed bytes, u64 n_blocks,
+ * then n_blocks + 1 u64 stream offsets, all little-endian.  Same FILE* ownership rules as the
+ * drop-in calls (caller opens and closes).                                                */
+int snappy_b200_compress_file_indexed(FILE *in, unsigned long long input_size, int mode, FILE *out, FILE *index_out);
+int snappy_b200_decompress_file_indexed(FILE *in, FILE *index_in, FILE *out);
 /* Releases the cached device/pinned buffers of the host-buffer API. */
 void snappy_b200_release(void);
 /* Page-locked host memory for the buffers handed to the host-buffer API (what the reference's

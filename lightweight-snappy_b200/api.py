@@ -55,6 +55,12 @@ SIGNATURES = {
     "snappy_b200_compress_host": (C.c_int, [_u8p, C.c_uint64, C.c_int, _u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "snappy_b200_uncompressed_length": (C.c_int, [_u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "snappy_b200_decompress_host": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "snappy_b200_compress_host_indexed": (C.c_int, [_u8p, C.c_uint64, C.c_int, _u8p, C.c_uint64, C.POINTER(C.c_uint64),
+                                                    _u8p]),
+    "snappy_b200_decompress_host_indexed": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, _u8p, C.c_uint64,
+                                                      C.POINTER(C.c_uint64)]),
+    "snappy_b200_compress_file_indexed": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p]),
+    "snappy_b200_decompress_file_indexed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snappy_b200_release": (None, []),
     "snappy_b200_host_alloc": (C.c_void_p, [C.c_size_t]),
     "snappy_b200_host_free": (None, [C.c_void_p]),
@@ -129,6 +135,29 @@ def compress_host(data, mode: int = MODE_HASH, out: np.ndarray | None = None) ->
         out = np.empty(max(cap, 1), dtype=np.uint8)
     n = C.c_uint64(0)
     _check(lib().snappy_b200_compress_host(a.ctypes.data, a.size, mode, out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value]
+
+
+def compress_host_indexed(data, mode: int = MODE_HASH) -> tuple[np.ndarray, np.ndarray]:
+    """Stream + side index (u64 block offsets, block_count + 1 entries)."""
+    a = _host_u8(data)
+    out = np.empty(max(max_compressed_bytes(a.size), 1), dtype=np.uint8)
+    offs = np.zeros(block_count(a.size) + 1, dtype=np.uint64)
+    n = C.c_uint64(0)
+    _check(lib().snappy_b200_compress_host_indexed(a.ctypes.data, a.size, mode, out.ctypes.data, out.size, C.byref(n),
+                                                   offs.ctypes.data))
+    return out[: n.value], offs
+
+
+def decompress_host_indexed(stream, block_offsets, out: np.ndarray | None = None) -> np.ndarray:
+    a = _host_u8(stream)
+    offs = np.ascontiguousarray(block_offsets, dtype=np.uint64)
+    total = uncompressed_length(a)
+    if out is None:
+        out = np.empty(max(total, 1), dtype=np.uint8)
+    n = C.c_uint64(0)
+    _check(lib().snappy_b200_decompress_host_indexed(a.ctypes.data, a.size, offs.ctypes.data, offs.size - 1,
+                                                     out.ctypes.data, out.size, C.byref(n)))
     return out[: n.value]
 
 

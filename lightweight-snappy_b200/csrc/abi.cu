@@ -137,6 +137,12 @@ cudaError_t compress_chunk(const uint8_t *d_in, uint64_t chunk_bytes, uint64_t v
     return e;
 }
 
+// The block offsets (relative to the chunk's output) compress_chunk left in its workspace: nb + 1 entries.
+const uint64_t *compress_chunk_offsets(void *d_workspace, uint64_t chunk_bytes)
+{
+    return carve_compress(d_workspace, chunk_bytes).offsets;
+}
+
 } // namespace sb200
 
 using namespace sb200;

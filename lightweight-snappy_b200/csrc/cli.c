@@ -17,11 +17,13 @@
 
 static void usage(void)
 {
-    fprintf(stderr, "snappy [-c|-d|-b] [-r] [infile] [outfile]\n"
+    fprintf(stderr, "snappy [-c|-d|-b] [-r] [-i] [infile] [outfile]\n"
                     "-c compress (hash table)\n"
                     "-b compress (exact-key / BST match finder)\n"
                     "-d decompress\n"
-                    "-r print sizes, ratio, time and throughput\n");
+                    "-r print sizes, ratio, time and throughput\n"
+                    "-i side index: compress also writes <outfile>.idx (block offsets; the stream is\n"
+                    "   unchanged), decompress reads <infile>.idx and skips the boundary search\n");
     exit(EXIT_FAILURE);
 }
 
@@ -43,15 +45,16 @@ static double now(void)
 int main(int argc, char *argv[])
 {
     enum { COMPRESS, COMPRESS_BST, UNCOMPRESS } mode = COMPRESS;
-    int report = 0, opt;
+    int report = 0, use_index = 0, opt;
     if (argc < 4)
         usage();
-    while ((opt = getopt(argc, argv, "cbdr")) != -1) {
+    while ((opt = getopt(argc, argv, "cbdri")) != -1) {
         switch (opt) {
         case 'c': mode = COMPRESS; break;
         case 'b': mode = COMPRESS_BST; break;
         case 'd': mode = UNCOMPRESS; break;
         case 'r': report = 1; break;
+        case 'i': use_index = 1; break;
         default: usage();
         }
     }
@@ -69,14 +72,33 @@ int main(int argc, char *argv[])
     }
     const unsigned long long in_size = file_size(in);
     int rc = 0;
+    FILE *idx = NULL;
+    if (use_index) {
+        char idx_name[4096];
+        snprintf(idx_name, sizeof idx_name, "%s.idx", mode == UNCOMPRESS ? in_name : out_name);
+        idx = fopen(idx_name, mode == UNCOMPRESS ? "rb" : "wb");
+        if (!idx) {
+            fprintf(stderr, "cannot open %s: %s\n", idx_name, strerror(errno));
+            fclose(in);
+            fclose(out);
+            return EXIT_FAILURE;
+        }
+    }
     const double t0 = now();
-    if (mode == COMPRESS)
+    if (idx && mode == UNCOMPRESS)
+        rc = snappy_b200_decompress_file_indexed(in, idx, out);
+    else if (idx)
+        rc = snappy_b200_compress_file_indexed(in, in_size, mode == COMPRESS ? SNAPPY_B200_MODE_HASH : SNAPPY_B200_MODE_BST,
+                                               out, idx);
+    else if (mode == COMPRESS)
         snappy_compress(in, in_size, out);
     else if (mode == COMPRESS_BST)
         rc = snappy_compress_bst(in, in_size, out);
     else
         rc = snappy_decompress(in, out);
     const double dt = now() - t0;
+    if (idx)
+        fclose(idx);
     fclose(in);
     fflush(out);
     const unsigned long long out_size = (unsigned long long)ftell(out);

@@ -79,7 +79,9 @@ bool read_all(FILE *f, uint64_t hint, PinnedBuf &buf)
     return true;
 }
 
-int compress_file(FILE *in, unsigned long long declared, FILE *out, int mode)
+const char kIndexMagic[8] = {'S', 'N', 'P', 'I', 'D', 'X', '1', 0};
+
+int compress_file(FILE *in, unsigned long long declared, FILE *out, int mode, FILE *index_out = nullptr)
 {
     PinnedBuf data, stream;
     if (!in || !out || !read_all(in, declared, data))
@@ -89,7 +91,16 @@ int compress_file(FILE *in, unsigned long long declared, FILE *out, int mode)
     if (!stream.reserve(snappy_b200_max_compressed_bytes(data.size())))
         return SNAPPY_B200_ERR_IO;
     uint64_t n = 0;
-    const int rc = snappy_b200_compress_host(data.data(), data.size(), mode, stream.data(), stream.cap, &n);
+    const uint64_t nb = snappy_b200_block_count(data.size());
+    uint64_t *offsets = index_out ? static_cast<uint64_t *>(malloc((nb + 1) * 8)) : nullptr;
+    if (index_out && !offsets)
+        return SNAPPY_B200_ERR_IO;
+    struct Free {
+        void *p;
+        ~Free() { free(p); }
+    } free_offsets{offsets};
+    const int rc =
+        snappy_b200_compress_host_indexed(data.data(), data.size(), mode, stream.data(), stream.cap, &n, offsets);
     if (rc != SNAPPY_B200_OK) {
         fprintf(stderr, "snappy_b200: %s\n", snappy_b200_last_error());
         return rc;
@@ -103,12 +114,62 @@ int compress_file(FILE *in, unsigned long long declared, FILE *out, int mode)
         return SNAPPY_B200_ERR_IO;
     if (fwrite(stream.data() + hdr_real, 1, n - hdr_real, out) != n - hdr_real)
         return SNAPPY_B200_ERR_IO;
+    if (index_out) {
+        // offsets as they are in the file just written (the declared-size preamble may be longer or shorter)
+        for (uint64_t b = 0; b <= nb; ++b)
+            offsets[b] = offsets[b] - hdr_real + hdr_decl;
+        const uint64_t head[2] = {data.size(), nb};
+        if (fwrite(kIndexMagic, 1, 8, index_out) != 8 || fwrite(head, 8, 2, index_out) != 2 ||
+            fwrite(offsets, 8, nb + 1, index_out) != nb + 1)
+            return SNAPPY_B200_ERR_IO;
+    }
     return SNAPPY_B200_OK;
 }
 
 } // namespace
 
 extern "C" {
+
+int snappy_b200_compress_file_indexed(FILE *in, unsigned long long input_size, int mode, FILE *out, FILE *index_out)
+{
+    return compress_file(in, input_size, out, mode, index_out);
+}
+
+int snappy_b200_decompress_file_indexed(FILE *in, FILE *index_in, FILE *out)
+{
+    PinnedBuf stream, data;
+    if (!in || !index_in || !out || !read_all(in, 0, stream))
+        return SNAPPY_B200_ERR_IO;
+    char magic[8];
+    uint64_t head[2];
+    if (fread(magic, 1, 8, index_in) != 8 || memcmp(magic, kIndexMagic, 8) != 0 || fread(head, 8, 2, index_in) != 2 ||
+        head[1] != snappy_b200_block_count(head[0]) || head[1] >= (1ull << 31)) {
+        fprintf(stderr, "snappy_b200: not a block index file\n");
+        return SNAPPY_B200_ERR_CORRUPT;
+    }
+    uint64_t *offsets = static_cast<uint64_t *>(malloc((head[1] + 1) * 8));
+    if (!offsets)
+        return SNAPPY_B200_ERR_IO;
+    int rc = SNAPPY_B200_OK;
+    if (fread(offsets, 8, head[1] + 1, index_in) != head[1] + 1) {
+        fprintf(stderr, "snappy_b200: truncated block index file\n");
+        rc = SNAPPY_B200_ERR_CORRUPT;
+    }
+    uint64_t n = 0;
+    if (rc == SNAPPY_B200_OK && head[0] && !data.reserve(head[0]))
+        rc = SNAPPY_B200_ERR_IO;
+    if (rc == SNAPPY_B200_OK && head[0]) {
+        rc = snappy_b200_decompress_host_indexed(stream.data(), stream.size(), offsets, head[1], data.data(), data.cap, &n);
+        if (rc == SNAPPY_B200_OK && n != head[0])
+            rc = SNAPPY_B200_ERR_CORRUPT;
+        if (rc == SNAPPY_B200_OK && fwrite(data.data(), 1, n, out) != n)
+            rc = SNAPPY_B200_ERR_IO;
+        else if (rc != SNAPPY_B200_OK)
+            fprintf(stderr, "snappy_b200: %s\n", snappy_b200_last_error());
+    }
+    free(offsets);
+    return rc;
+}
 
 void snappy_compress(FILE *file_input, unsigned long long input_size, FILE *file_compressed)
 {

@@ -44,6 +44,9 @@ cudaError_t run_index(const uint8_t *, uint64_t, uint64_t, uint64_t, uint64_t *,
                       uint64_t *, bool, uint64_t);
 const uint4 *index_starts(void *, uint64_t);
 const uint64_t *index_total(void *, uint64_t);
+const uint64_t *compress_chunk_offsets(void *, uint64_t);
+cudaError_t launch_decode(const uint8_t *, const uint64_t *, uint64_t, uint64_t, uint8_t *, uint32_t *, cudaStream_t,
+                          uint64_t *);
 cudaError_t launch_decode_seg(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, uint64_t, uint64_t, uint8_t *,
                               uint32_t *, cudaStream_t, uint64_t *);
 
@@ -338,6 +341,12 @@ extern "C" {
 int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
                               uint64_t *out_bytes)
 {
+    return snappy_b200_compress_host_indexed(in, n_bytes, mode, out, out_capacity, out_bytes, nullptr);
+}
+
+int snappy_b200_compress_host_indexed(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
+                                      uint64_t *out_bytes, uint64_t *block_offsets)
+{
     if (!out_bytes || (n_bytes && (!in || !out)))
         return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
     if (mode != SNAPPY_B200_MODE_HASH && mode != SNAPPY_B200_MODE_BST)
@@ -402,6 +411,7 @@ int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *
     };
 
     uint64_t off = 0, issued = 0;
+    std::vector<uint64_t> chunk_off(n_chunks); // where each chunk landed in the caller's buffer
     for (uint64_t j = 0; j < n_chunks; ++j) {
         while (issued < n_chunks && issued < j + (uint64_t)slots)
             CU(issue(issued++), "compress launch");
@@ -419,12 +429,27 @@ int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *
         }
         CU(cudaStreamWaitEvent(g_ctx.s_down, ev_run[s], 0), "stream wait");
         CU(cudaMemcpyAsync(dst + off, g_ctx.buf[4 + s], clen, cudaMemcpyDeviceToHost, g_ctx.s_down), "D2H copy");
+        if (block_offsets) { // the chunk's offsets, chunk-relative for now (entry nb of chunk j = entry 0 of chunk j+1)
+            const uint64_t lo = j * chunk, len = std::min(chunk, n_bytes - lo);
+            CU(cudaMemcpyAsync(block_offsets + lo / kBlock, compress_chunk_offsets(g_ctx.buf[8 + s], len),
+                               ((len + kBlock - 1) / kBlock + 1) * 8, cudaMemcpyDeviceToHost, g_ctx.s_down),
+               "D2H copy");
+        }
+        chunk_off[j] = off;
         CU(cudaEventRecord(ev_down[s], g_ctx.s_down), "event record");
         trace.mark("download done, chunk " + std::to_string(j) + " (" + std::to_string(clen >> 20) + " MiB)", g_ctx.s_down);
         off += clen;
     }
     CU(cudaStreamSynchronize(g_ctx.s_down), "D2H copy");
     trace.dump();
+    if (block_offsets) {
+        for (uint64_t j = 0; j < n_chunks; ++j) {
+            const uint64_t b0 = j * chunk / kBlock, b1 = std::min((j + 1) * chunk, align_up(n_bytes, kBlock)) / kBlock;
+            for (uint64_t b = b0; b < b1; ++b)
+                block_offsets[b] += chunk_off[j];
+        }
+        block_offsets[(n_bytes + kBlock - 1) / kBlock] = off;
+    }
     *out_bytes = off;
     return SNAPPY_B200_OK;
 }
@@ -543,6 +568,85 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
     CU(cudaStreamSynchronize(g_ctx.s_run), "decode");
     CU(cudaStreamSynchronize(g_ctx.s_down), "D2H copy");
     trace.dump();
+    const uint32_t status = (uint32_t)g_ctx.h_small[1];
+    if (status)
+        return status_error(status);
+    *out_bytes = total;
+    return SNAPPY_B200_OK;
+}
+
+// ---- decode with the side index: no K0.  The stream goes up in pieces cut at block boundaries
+// (growing like the index-less path's), every piece is decoded by the window decoder as soon as it
+// has landed and downloaded while the next one is in flight.
+int snappy_b200_decompress_host_indexed(const void *stream, uint64_t stream_bytes, const uint64_t *block_offsets,
+                                        uint64_t n_blocks, void *out, uint64_t out_capacity, uint64_t *out_bytes)
+{
+    if (!out_bytes || (stream_bytes && !stream) || !block_offsets)
+        return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    *out_bytes = 0;
+    if (stream_bytes == 0)
+        return SNAPPY_B200_OK;
+    uint64_t total = 0;
+    const unsigned hdr = host_varint_decode(static_cast<const uint8_t *>(stream), stream_bytes, &total);
+    if (!hdr)
+        return fail_msg(SNAPPY_B200_ERR_CORRUPT, "bad varint preamble");
+    if (total > out_capacity)
+        return fail_msg(SNAPPY_B200_ERR_CAPACITY, "output buffer too small for the decompressed data");
+    if (n_blocks != (total + kBlock - 1) / kBlock || n_blocks >= (1ull << 31))
+        return fail_msg(SNAPPY_B200_ERR_ARG, "the index does not have one entry per 64 KiB block of the declared length");
+    if (total == 0)
+        return stream_bytes == hdr ? SNAPPY_B200_OK
+                                   : fail_msg(SNAPPY_B200_ERR_CORRUPT, "trailing bytes after an empty stream");
+    if (!out)
+        return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    if (block_offsets[0] != hdr || block_offsets[n_blocks] != stream_bytes)
+        return fail_msg(SNAPPY_B200_ERR_CORRUPT, "the index does not span the stream");
+    for (uint64_t b = 0; b < n_blocks; ++b)
+        if (block_offsets[b + 1] <= block_offsets[b] || block_offsets[b + 1] - block_offsets[b] > 2u * kBlock)
+            return fail_msg(SNAPPY_B200_ERR_CORRUPT, "the index is not increasing / a block is larger than any 64 KiB block can be");
+
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    CU(g_ctx.init(), "context init");
+    CU(g_ctx.need(0, stream_bytes + 64), "cudaMalloc");
+    CU(g_ctx.need(1, total), "cudaMalloc");
+    CU(g_ctx.need(4, (n_blocks + 2) * 8), "cudaMalloc");
+    CU(g_ctx.need(6, 256), "cudaMalloc");
+    uint8_t *d_stream = static_cast<uint8_t *>(g_ctx.buf[0]);
+    uint8_t *d_out = static_cast<uint8_t *>(g_ctx.buf[1]);
+    uint64_t *d_offs = static_cast<uint64_t *>(g_ctx.buf[4]);
+    uint32_t *d_status = static_cast<uint32_t *>(g_ctx.buf[6]);
+    const uint8_t *src = static_cast<const uint8_t *>(stream);
+    uint8_t *dst = static_cast<uint8_t *>(out);
+    CU(cudaMemsetAsync(d_status, 0, 4, g_ctx.s_up), "memset");
+    CU(cudaMemcpyAsync(d_offs, block_offsets, (n_blocks + 1) * 8, cudaMemcpyHostToDevice, g_ctx.s_up), "H2D copy");
+    uint64_t launches = 0;
+    const uint64_t piece = kUploadPiece;
+    uint64_t b0 = 0, want = std::max<uint64_t>(piece / 8, 1 << 20);
+    int k = 0;
+    while (b0 < n_blocks) {
+        // blocks [b0, b1): about `want` stream bytes
+        uint64_t b1 = std::upper_bound(block_offsets + b0, block_offsets + n_blocks, block_offsets[b0] + want) - block_offsets;
+        b1 = std::min(std::max(b1, b0 + 1), n_blocks);
+        const uint64_t lo = b0 ? block_offsets[b0] : 0, hi = block_offsets[b1];
+        cudaEvent_t ev_up = g_ctx.ev[k & 7], ev_dec = g_ctx.ev[8 + (k & 7)];
+        CU(cudaMemcpyAsync(d_stream + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, g_ctx.s_up), "H2D copy");
+        CU(cudaEventRecord(ev_up, g_ctx.s_up), "event record");
+        CU(cudaStreamWaitEvent(g_ctx.s_dec, ev_up, 0), "stream wait");
+        const uint64_t out_lo = b0 * kBlock, out_n = std::min(total, b1 * (uint64_t)kBlock) - out_lo;
+        CU(launch_decode(d_stream, d_offs + b0, b1 - b0, out_n, d_out + out_lo, d_status, g_ctx.s_dec, &launches),
+           "decode launch");
+        CU(cudaEventRecord(ev_dec, g_ctx.s_dec), "event record");
+        CU(cudaStreamWaitEvent(g_ctx.s_down, ev_dec, 0), "stream wait");
+        CU(cudaMemcpyAsync(dst + out_lo, d_out + out_lo, out_n, cudaMemcpyDeviceToHost, g_ctx.s_down), "D2H copy");
+        b0 = b1;
+        want = std::min(want * 2, piece);
+        ++k;
+    }
+    add_launches(launches);
+    CU(cudaStreamSynchronize(g_ctx.s_dec), "decode");
+    CU(peek_u32(reinterpret_cast<uint32_t *>(g_ctx.h_small + 1), d_status, 1, g_ctx.s_dec), "read-back");
+    CU(cudaStreamSynchronize(g_ctx.s_dec), "decode");
+    CU(cudaStreamSynchronize(g_ctx.s_down), "D2H copy");
     const uint32_t status = (uint32_t)g_ctx.h_small[1];
     if (status)
         return status_error(status);

@@ -307,3 +307,46 @@ def test_shared_memory_table_variant(oracle, monkeypatch):
         data = datasets.gen(spec)
         for mode, fn in ((0, api.snappy_compress), (1, api.snappy_compress_bst)):
             _assert_same(fn(data), oracle.compress(data, mode), f"{spec} mode {mode} (shared-memory tables)")
+
+
+@pytest.mark.gpu
+def test_side_index_host_api(oracle, monkeypatch):
+    """the optional side index.  The stream is unchanged, the index equals the
+    oracle's block index, the indexed decoder (no K0) inverts it, and a wrong index is reported."""
+    monkeypatch.setenv("SNAPPY_B200_CHUNK_MIB", "4")   # several compress chunks
+    monkeypatch.setenv("SNAPPY_B200_PIECE_MIB", "8")   # several decode pieces
+    for spec in ("corpus:mixed:0:0:20000000", "corpus:text:1:100:65536", "corpus:lowent:2:0:65537", "hex:616263",
+                 "corpus:random:5:0:1000000"):
+        data = datasets.gen(spec)
+        for mode in (0, 1):
+            want = oracle.compress(data, mode)
+            stream, offs = api.compress_host_indexed(data, mode)
+            _assert_same(stream, want, f"{spec} mode {mode}: stream with index")
+            ref_idx, _ = oracle.block_index(want)
+            assert offs.tolist() == [int(x) for x in ref_idx], f"{spec} mode {mode}: index"
+            _assert_same(api.decompress_host_indexed(stream, offs), data, f"{spec} mode {mode}: indexed decode")
+    data = datasets.gen("corpus:mixed:0:0:400000")
+    stream, offs = api.compress_host_indexed(data, 0)
+    bad = offs.copy()
+    bad[3] += 1
+    with pytest.raises(api.SnappyError):
+        api.decompress_host_indexed(stream, bad)
+    bad = offs.copy()
+    bad[2], bad[3] = offs[3], offs[2]
+    with pytest.raises(api.SnappyError):
+        api.decompress_host_indexed(stream, bad)
+
+
+@pytest.mark.gpu
+def test_cli_side_index(tmp_path):
+    data = datasets.gen("corpus:mixed:0:0:5000000")
+    src, comp, back, plain = tmp_path / "in", tmp_path / "c.snp", tmp_path / "back", tmp_path / "plain.snp"
+    src.write_bytes(data.tobytes())
+    import subprocess
+    subprocess.run([api.CLI_PATH, "-c", "-i", str(src), str(comp)], check=True, timeout=300)
+    subprocess.run([api.CLI_PATH, "-c", str(src), str(plain)], check=True, timeout=300)
+    assert comp.read_bytes() == plain.read_bytes(), "-i must not change the stream"
+    idx = (tmp_path / "c.snp.idx").read_bytes()
+    assert idx[:8] == b"SNPIDX1\0" and len(idx) == 24 + 8 * (api.block_count(data.size) + 1)
+    subprocess.run([api.CLI_PATH, "-d", "-i", str(comp), str(back)], check=True, timeout=300)
+    assert back.read_bytes() == data.tobytes()
