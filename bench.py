@@ -186,6 +186,7 @@ def run_gpu_arm(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     base = None

@@ -362,6 +362,12 @@ __global__ void __launch_bounds__(32) k_decode_seg(const uint8_t *__restrict__ s
         const uint4 sv = __ldg(starts + t);
         uint32_t R[4] = {sv.x, sv.y, sv.z, sv.w};
         const uint32_t seg_lo = (uint32_t)((t - t0) * kSegBytes);
+        // the block is one serial chain: have the stream (and its maps) on their way before they are needed
+        if (((t - t0) & 7u) == 0 && t + 8 + lane <= t1) {
+            prefetch_l2(in + seg_lo + (8 + lane) * kSegBytes);
+            if (lane < 4)
+                prefetch_l2(starts + t + 8 + 8 * lane);
+        }
         // keep only the starts that belong to this block (only the first / last segment can hold others)
         if (t == t0 || t == t1)
 #pragma unroll

@@ -51,6 +51,7 @@ def main() -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     import oracle_lib  # tests/oracle_lib.py: the checker, never the thing measured
