@@ -324,18 +324,23 @@ __device__ __forceinline__ void produce_run(uint8_t *out, uint32_t op, uint32_t 
     }
 }
 
-__global__ void __launch_bounds__(32) k_decode_seg(const uint8_t *__restrict__ stream, uint64_t body_offset,
-                                                   const uint64_t *__restrict__ offsets,
-                                                   const uint4 *__restrict__ starts, uint64_t total_out,
-                                                   uint8_t *out_base, uint32_t *__restrict__ status)
+template <int MINB>
+__global__ void __launch_bounds__(64, MINB) k_decode_seg(const uint8_t *__restrict__ stream, uint64_t body_offset,
+                                                         const uint64_t *__restrict__ offsets,
+                                                         const uint4 *__restrict__ starts, uint64_t total_out,
+                                                         uint8_t *out_base, uint32_t *__restrict__ status,
+                                                         uint64_t n_blocks)
 {
-    __shared__ SegSmem sm;
-    const uint32_t lane = threadIdx.x;
-    const uint64_t blk = blockIdx.x;
+    __shared__ SegSmem sm2[2];
+    SegSmem &sm = sm2[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t blk = blockIdx.x * 2ull + (threadIdx.x >> 5);
+    if (blk >= n_blocks)
+        return;
     if (*reinterpret_cast<volatile uint32_t *>(status) != 0)
         return; // K0 rejected the stream: its maps are not trustworthy
     const uint64_t c0 = offsets[blk], c1 = offsets[blk + 1];
-    const uint64_t stream_bytes = offsets[gridDim.x];
+    const uint64_t stream_bytes = offsets[n_blocks];
     if (c1 <= c0 || c0 < body_offset || c1 > stream_bytes || c1 - c0 > 2u * kBlock) {
         if (lane == 0)
             atomicOr(status, SNAPPY_B200_ST_CORRUPT);
@@ -617,8 +622,10 @@ cudaError_t launch_decode_seg(const uint8_t *d_stream, uint64_t body_offset, con
         return cudaSuccess;
     if (n_blocks > 0x7fffffffull)
         return cudaErrorInvalidValue;
-    k_decode_seg<<<(unsigned)n_blocks, 32, 0, st>>>(d_stream, body_offset, d_offsets, d_starts, total_out, d_out,
-                                                    d_status);
+    // two blocks (warps) per CTA and a 48-register cap: 40 warps per SM instead of the 32 that one-warp
+    // CTAs allow (measured: 64 registers / 32 warps 6.92, 48 / 40 6.72, 40 / 48 6.84 ms per GiB, K0 included)
+    k_decode_seg<20><<<(unsigned)((n_blocks + 1) / 2), 64, 0, st>>>(d_stream, body_offset, d_offsets, d_starts, total_out,
+                                                                    d_out, d_status, n_blocks);
     *launches += 1;
     return cudaGetLastError();
 }
