@@ -409,16 +409,18 @@ __global__ void __launch_bounds__(64, MINB) k_decode_seg(const uint8_t *__restri
             len0 = (((v0 >> 8) | ((pos0 + 4 < lim ? (uint32_t)__ldg(in + pos0 + 4) : 0u) << 24))) + 1u;
         if (has1 && h1.is_lit && h1.hdr == 5)
             len1 = (((v1 >> 8) | ((pos1 + 4 < lim ? (uint32_t)__ldg(in + pos1 + 4) : 0u) << 24))) + 1u;
-        // output offsets: 64-bit sums, so that absurd literal lengths cannot wrap around
-        uint64_t end = (uint64_t)len0 + len1;
+        // output offsets.  Lengths are clamped to one more than a block can hold before they are
+        // summed (an absurd literal length cannot wrap the sum, and still trips the T > room test)
+        const uint32_t lc0 = min(len0, kBlock + 1u), lc1 = min(len1, kBlock + 1u);
+        uint32_t end = lc0 + lc1;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint64_t u = __shfl_up_sync(kFull, end, d);
+            const uint32_t u = __shfl_up_sync(kFull, end, d);
             if ((int)lane >= d)
                 end += u;
         }
-        const uint64_t T64 = __shfl_sync(kFull, end, 31);
-        const uint32_t start0 = (uint32_t)(end - len0 - len1), start1 = start0 + len0;
+        const uint32_t T64 = __shfl_sync(kFull, end, 31);
+        const uint32_t start0 = end - lc0 - lc1, start1 = start0 + lc0;
         const bool corrupt0 = has0 && (pos0 + h0.hdr > lim || (h0.is_lit && (uint64_t)pos0 + h0.hdr + len0 > lim) ||
                                        (!h0.is_lit && !h0.slow && h0.info == 0));
         const bool corrupt1 = has1 && (pos1 + h1.hdr > lim || (h1.is_lit && (uint64_t)pos1 + h1.hdr + len1 > lim) ||
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(64, MINB) k_decode_seg(const uint8_t *__restri
             err = BC ? SNAPPY_B200_ST_CORRUPT : SNAPPY_B200_ST_FRAMING;
             break;
         }
-        const uint32_t T = (uint32_t)T64;
+        const uint32_t T = T64;
         const unsigned S = __ballot_sync(kFull, sp0 || sp1);
         // ---- the table
         if (has0) {
