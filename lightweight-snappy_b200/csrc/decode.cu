@@ -368,10 +368,12 @@ __global__ void __launch_bounds__(64, MINB) k_decode_seg(const uint8_t *__restri
         uint32_t R[4] = {sv.x, sv.y, sv.z, sv.w};
         const uint32_t seg_lo = (uint32_t)((t - t0) * kSegBytes);
         // the block is one serial chain: have the stream (and its maps) on their way before they are needed
-        if (((t - t0) & 7u) == 0 && t + 8 + lane <= t1) {
-            prefetch_l2(in + seg_lo + (8 + lane) * kSegBytes);
-            if (lane < 4)
-                prefetch_l2(starts + t + 8 + 8 * lane);
+        // (every 8 segments: the 8 stream lines 16..23 segments ahead, one lane each, and the line of their maps)
+        if (((t - t0) & 7u) == 0 && lane <= 8 && t + 16 + lane <= t1) {
+            if (lane < 8)
+                prefetch_l2(in + seg_lo + (16 + lane) * kSegBytes);
+            else
+                prefetch_l2(starts + t + 16);
         }
         // keep only the starts that belong to this block (only the first / last segment can hold others)
         if (t == t0 || t == t1)
