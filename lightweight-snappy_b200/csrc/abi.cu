@@ -16,9 +16,10 @@ cudaError_t launch_compact(const uint8_t *, const uint32_t *, uint64_t, uint64_t
                            uint64_t *, uint64_t *, uint32_t *, cudaStream_t, uint64_t *);
 cudaError_t launch_decode(const uint8_t *, const uint64_t *, uint64_t, uint64_t, uint8_t *, uint32_t *, cudaStream_t,
                           uint64_t *);
-cudaError_t launch_decode_seg(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, uint64_t, uint64_t, uint8_t *,
-                              uint32_t *, cudaStream_t, uint64_t *);
+cudaError_t launch_decode_seg(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, const uint64_t *, uint64_t,
+                              uint64_t, uint8_t *, uint32_t *, uint64_t, cudaStream_t, uint64_t *);
 const uint4 *index_starts(void *, uint64_t);
+const uint64_t *index_outoff(void *, uint64_t);
 size_t index_workspace_bytes(uint64_t);
 cudaError_t run_index(const uint8_t *, uint64_t, uint64_t, uint64_t, uint64_t *, uint32_t *, void *, cudaStream_t,
                       uint64_t *, bool, uint64_t);
@@ -259,8 +260,8 @@ int snappy_b200_decode_segments_device(const uint8_t *d_stream, uint64_t stream_
         return fail(SNAPPY_B200_ERR_ARG, "workspace too small");
     uint64_t launches = 0;
     cudaError_t e = launch_decode_seg(d_stream, body_offset, d_block_offsets, index_starts(d_workspace, stream_bytes),
-                                      (total_out + kBlock - 1) / kBlock, total_out, d_out, d_status,
-                                      static_cast<cudaStream_t>(stream), &launches);
+                                      index_outoff(d_workspace, stream_bytes), (total_out + kBlock - 1) / kBlock,
+                                      total_out, d_out, d_status, 0, static_cast<cudaStream_t>(stream), &launches);
     g_launches += launches;
     if (e != cudaSuccess)
         return cuda_fail(e, "decode launch");

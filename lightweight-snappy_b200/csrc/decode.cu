@@ -28,7 +28,10 @@
 //                  decodes the byte at its offset as if an element started there, and the
 //                  real starts are the orbit of lane 0 under "next = lane + element size",
 //                  found with pointer doubling over shuffles and five warp-wide OR reductions.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "tags.cuh"
 
 namespace sb200 {
 
@@ -47,13 +50,6 @@ __device__ __forceinline__ uint32_t ld_le32_any(const uint8_t *__restrict__ p, c
     return __funnelshift_r(__ldg(w0), __ldg(w1), (uint32_t)(a & 3u) * 8u);
 }
 
-struct Header {
-    uint32_t hdr;  // header bytes (tag + extra)
-    uint32_t len;  // output bytes
-    uint32_t info; // literal: stream position of its bytes; copy: offset
-    bool is_lit;
-    bool slow; // header does not fit in the 4 bytes of v
-};
 
 // Decodes the element whose first 4 stream bytes are v and whose tag sits at stream position pos.
 __device__ __forceinline__ Header decode_header(uint32_t v, uint32_t pos)
@@ -236,44 +232,6 @@ __device__ __forceinline__ uint32_t run_step(const uint8_t *__restrict__ in, uin
 // prefix sum over the per-lane sums.
 constexpr uint32_t kSegElems = 64;
 constexpr uint32_t kRunBytes = kSegElems * 64; // output bytes of a run of ordinary elements (each <= 64)
-
-// Tag byte -> header facts, looked up instead of branched over (two headers per lane per step):
-//   bits 0-2 header bytes, bits 3-9 output length when the tag alone gives it (0: a literal whose
-//   length follows in 1..4 bytes), bit 10 literal, bit 11 needs the one-element path whatever its
-//   length (copy-4, 4-byte literal length), bit 12 copy with a 1-byte offset.
-constexpr uint32_t kTagLit = 1u << 10, kTagSlow = 1u << 11, kTagCopy1 = 1u << 12;
-
-__device__ __forceinline__ uint32_t tag_facts(uint32_t tag)
-{
-    const uint32_t type = tag & 3u, m = tag >> 2;
-    if (type == 0) {
-        if (m < 60)
-            return 1u | ((m + 1u) << 3) | kTagLit;
-        const uint32_t k = m - 59u; // length bytes
-        return (1u + k) | kTagLit | (k == 4 ? kTagSlow : 0u);
-    }
-    if (type == 1)
-        return 2u | (((m & 7u) + 4u) << 3) | kTagCopy1;
-    if (type == 2)
-        return 3u | ((m + 1u) << 3);
-    return 5u | ((m + 1u) << 3) | kTagSlow;
-}
-
-// The same element facts as decode_header() from the table (v = the 4 stream bytes at pos).
-__device__ __forceinline__ Header decode_header_lut(const uint16_t *__restrict__ lut, uint32_t v, uint32_t pos)
-{
-    Header h;
-    const uint32_t f = lut[v & 0xffu];
-    h.hdr = f & 7u;
-    h.len = (f >> 3) & 127u;
-    h.is_lit = f & kTagLit;
-    h.slow = f & kTagSlow;
-    if (h.len == 0) // literal with 1..4 length bytes (the fourth one does not fit v: the caller's business)
-        h.len = ((v >> 8) & (0xffffffu >> (8u * (4u - min(h.hdr, 4u))))) + 1u;
-    const uint32_t c1 = ((v << 3) & 0x700u) | ((v >> 8) & 0xffu), c2 = (v >> 8) & 0xffffu;
-    h.info = h.is_lit ? pos + h.hdr : ((f & kTagCopy1) ? c1 : c2);
-    return h;
-}
 
 struct SegSmem {
     uint16_t lut[256];
@@ -618,14 +576,28 @@ cudaError_t launch_decode(const uint8_t *d_stream, const uint64_t *d_offsets, ui
     return cudaGetLastError();
 }
 
+cudaError_t launch_decode_tile(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, const uint64_t *, uint64_t,
+                               uint64_t, uint8_t *, uint32_t *, uint64_t, cudaStream_t, uint64_t *); // decode_tile.cu
+
+// Decoder for the maps K0 leaves behind.  The tile decoder (one CTA per block, output block resident in
+// shared memory) is the product path; SNAPPY_B200_DECODER=seg selects the warp-per-block decoder that
+// writes straight to global memory (kept for A/B measurements).
 cudaError_t launch_decode_seg(const uint8_t *d_stream, uint64_t body_offset, const uint64_t *d_offsets,
-                              const uint4 *d_starts, uint64_t n_blocks, uint64_t total_out, uint8_t *d_out,
-                              uint32_t *d_status, cudaStream_t st, uint64_t *launches)
+                              const uint4 *d_starts, const uint64_t *d_outoff, uint64_t n_blocks, uint64_t total_out,
+                              uint8_t *d_out, uint32_t *d_status, uint64_t blk_base, cudaStream_t st,
+                              uint64_t *launches)
 {
     if (n_blocks == 0)
         return cudaSuccess;
     if (n_blocks > 0x7fffffffull)
         return cudaErrorInvalidValue;
+    static const bool use_seg = [] {
+        const char *v = getenv("SNAPPY_B200_DECODER");
+        return v && v[0] == 's';
+    }();
+    if (!use_seg)
+        return launch_decode_tile(d_stream, body_offset, d_offsets, d_starts, d_outoff, n_blocks, total_out, d_out,
+                                  d_status, blk_base, st, launches);
     // two blocks (warps) per CTA and a 48-register cap: 40 warps per SM instead of the 32 that one-warp
     // CTAs allow (measured: 64 registers / 32 warps 6.92, 48 / 40 6.72, 40 / 48 6.84 ms per GiB, K0 included)
     k_decode_seg<20><<<(unsigned)((n_blocks + 1) / 2), 64, 0, st>>>(d_stream, body_offset, d_offsets, d_starts, total_out,

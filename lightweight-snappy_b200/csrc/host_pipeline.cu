@@ -47,8 +47,9 @@ const uint64_t *index_total(void *, uint64_t);
 const uint64_t *compress_chunk_offsets(void *, uint64_t);
 cudaError_t launch_decode(const uint8_t *, const uint64_t *, uint64_t, uint64_t, uint8_t *, uint32_t *, cudaStream_t,
                           uint64_t *);
-cudaError_t launch_decode_seg(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, uint64_t, uint64_t, uint8_t *,
-                              uint32_t *, cudaStream_t, uint64_t *);
+const uint64_t *index_outoff(void *, uint64_t);
+cudaError_t launch_decode_seg(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, const uint64_t *, uint64_t, uint64_t, uint8_t *,
+                              uint32_t *, uint64_t, cudaStream_t, uint64_t *);
 
 namespace {
 
@@ -301,8 +302,8 @@ int decode_pieces(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t hdr, 
         }
         // decode on its own stream: K0 of the next piece does not wait for it
         CUP(cudaStreamWaitEvent(r.s_dec, r.ev_k0[s], 0), "stream wait");
-        CUP(launch_decode_seg(d_stream + rs, 0, r.offs[s], index_starts(r.ws[s], region), kdone, out_bytes_now,
-                              d_out + ob * kBlock, d_status, r.s_dec, &launches),
+        CUP(launch_decode_seg(d_stream + rs, 0, r.offs[s], index_starts(r.ws[s], region), index_outoff(r.ws[s], region),
+                              kdone, out_bytes_now, d_out + ob * kBlock, d_status, ob, r.s_dec, &launches),
             "decode launch");
         CUP(cudaEventRecord(r.ev_dec[s], r.s_dec), "event record");
         if (hooks.trace)

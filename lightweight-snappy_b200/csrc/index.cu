@@ -819,6 +819,8 @@ static IndexWorkspace carve(void *ws, uint64_t stream_bytes)
 
 // The exact element-start maps k_group_final leaves behind (one uint4 per 128-byte segment).
 const uint4 *index_starts(void *d_ws, uint64_t stream_bytes) { return carve(d_ws, stream_bytes).paths; }
+// Output offset of the first element that starts in each segment (exclusive scan of the segment output lengths).
+const uint64_t *index_outoff(void *d_ws, uint64_t stream_bytes) { return carve(d_ws, stream_bytes).outoff; }
 
 static uint64_t g_last_rounds = 0;
 uint64_t index_last_rounds() { return g_last_rounds; }
