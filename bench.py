@@ -43,21 +43,26 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 GIB = 1 << 30
 SEED = 20261018
 METRIC = "decompress GB/s (uncompressed)"
+DECODE_KERNEL = "k_decode_win (+ k_copy_literal_blocks)"
 
 
 # ------------------------------------------------------------------------------ CPU baseline
 def _cpu_worker(args):
-    """One host core: generate a shard of the mixed corpus, then time the CPU codec on it."""
-    shard, n_bytes, use_ref = args
+    """One host core: generate a shard of the corpus, then time the CPU codec on it."""
+    shard, n_bytes, use_ref, kind, mode, cpu = args
     import numpy as np
     import torch
     torch.set_num_threads(1)
+    try:  # one worker per core, pinned: the aggregate stops depending on where the scheduler puts them
+        os.sched_setaffinity(0, {cpu})
+    except (AttributeError, OSError):
+        pass
     from lightweight_snappy_b200 import corpus
     import oracle_lib
-    data = corpus.make_corpus("mixed", n_bytes, seed=SEED, first_segment=shard * (n_bytes >> 20)).numpy()
+    data = corpus.make_corpus(kind, n_bytes, seed=SEED, first_segment=shard * (n_bytes >> 20)).numpy()
     codec = oracle_lib.Reference() if use_ref else oracle_lib.Oracle()
     t0 = time.perf_counter()
-    stream = codec.compress(data, 0)
+    stream = codec.compress(data, mode)
     t1 = time.perf_counter()
     back = codec.decompress(stream, data.size)
     t2 = time.perf_counter()
@@ -65,25 +70,33 @@ def _cpu_worker(args):
     return {"n": int(data.size), "c": int(stream.size), "t_comp": t1 - t0, "t_decomp": t2 - t1, "ok": ok}
 
 
-def cpu_baseline(sample_mib_per_core: int = 48, cores: int | None = None) -> dict:
-    """Reference CPU codec, one process per host core, each on its own shard."""
+def cpu_baseline(sample_mib_per_core: int = 48, cores: int | None = None, kind: str = "mixed", mode: int = 0) -> dict:
+    """Reference CPU codec, one pinned process per host core, each on its own shard.
+    The sample is BOUNDED (cores x sample_mib_per_core MiB of the same corpus generator), not the
+    whole 1 GiB workload: the CPU codec's throughput does not depend on the input size."""
     import multiprocessing as mp
     import oracle_lib
     if not os.path.exists(oracle_lib.ORACLE_SO):
         oracle_lib.build(ref=False)
     use_ref = oracle_lib.Reference.available()
-    cores = cores or os.cpu_count() or 1
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cpus = list(range(os.cpu_count() or 1))
+    cores = min(cores or len(cpus), len(cpus))
     n = sample_mib_per_core << 20
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(i, n, use_ref) for i in range(cores)])
+        res = pool.map(_cpu_worker, [(i, n, use_ref, kind, mode, cpus[i]) for i in range(cores)], chunksize=1)
     total = sum(r["n"] for r in res)
     t_d = max(r["t_decomp"] for r in res)
     t_c = max(r["t_comp"] for r in res)
     return {
         "value": total / t_d / 1e9, "unit": "GB/s", "cores": cores, "kind": "reference" if use_ref else "port",
-        "sample": f"{cores} x {sample_mib_per_core} MiB shards of the mixed corpus, one process per core, "
+        "sample": f"bounded sample: {cores} x {sample_mib_per_core} MiB shards of the {kind} corpus (same generator and "
+                  f"seed as the GPU arm's 1 GiB), one pinned process per core, mode {'bst' if mode else 'hash'}, "
                   f"aggregate = total bytes / slowest process",
+        "shard_compressed_bytes": [r["c"] for r in res], "shard_mib": sample_mib_per_core,
         "compress_value": total / t_c / 1e9,
         "single_core_decompress": res[0]["n"] / res[0]["t_decomp"] / 1e9,
         "single_core_compress": res[0]["n"] / res[0]["t_comp"] / 1e9,
@@ -156,7 +169,10 @@ def run_reference_arm(args) -> None:
         "warmup": warm, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": "mixed corpus (text/low-entropy/random, 1 MiB segments), decompression, "
-                               "reference CPU build on all host cores, bounded sample"},
+                               "reference CPU build on all host cores; BOUNDED SAMPLE of the GPU arm's 1 GiB workload "
+                               "(16 x 48 MiB shards per step, same generator and seed) -- CPU throughput is "
+                               "size-independent, so config and step count differ from the GPU arm by design",
+                   "spread": {"min": min(vals), "max": max(vals), "samples": len(vals)}},
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "compress": {"value": base["compress_value"], "unit": "GB/s"},
@@ -230,12 +246,12 @@ def run_gpu_arm(args) -> None:
 
     def step_decompress(ev=None):
         # the call a user makes for a device-resident, index-less stream: K0 (boundary discovery)
-        # + segment-driven decode, pipelined in 128 MiB pieces inside the library
+        # + block decode (a device-resident stream is decoded in one piece)
         codec.decompress(stream, c_bytes, hdr, n, out, k0_index)
 
     def step_decode_kernel(ev=None):
-        # the two halves called separately over the whole stream, so that the dominant kernel
-        # (k_decode_seg, one launch over all 16384 blocks) is bracketed by its own pair of events
+        # the two halves called separately over the whole stream, so that the dominant kernel pair
+        # (k_copy_literal_blocks + k_decode_win, one launch each over all 16384 blocks) is bracketed by its own pair of events
         codec.index(stream, c_bytes, hdr, n, k0_index)
         if ev:
             ev[0].record()
@@ -282,15 +298,58 @@ def run_gpu_arm(args) -> None:
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         time.sleep(1.0)
-    td = timed(step_decompress, "k_decode_seg")
+    td = timed(step_decompress, DECODE_KERNEL)
     codec.check_status()
     assert torch.equal(out, data), "round trip failed (pipelined path)"
-    tk = timed(step_decode_kernel, "k_decode_seg")
+    tk = timed(step_decode_kernel, DECODE_KERNEL)
     codec.check_status()
     td["kernel_ms"] = tk["kernel_ms"]
     td["unpipelined_ms_per_step"] = tk["total_ms"] / args.steps
     tc = timed(step_compress, "k_parse_hash_global (+ k_emit + k_scan_sizes + k_gather)")
     codec.check_status()
+
+    # ---- BASELINE configs[3]: the BST (exact-key) path on 1 GiB of low-entropy + random data
+    tb = None
+    if not args.no_bst:
+        data_b = corpus.make_corpus("lowent_random", n, seed=SEED, device=dev, first_segment=seg0)
+
+        def step_bst(ev=None):
+            if ev:
+                ev[0].record()
+            codec.compress(data_b, api.MODE_BST)
+            if ev:
+                ev[1].record()
+
+        step_bst()
+        codec.check_status()
+        stream_b = codec.result_stream().clone()
+        cb_bytes = stream_b.numel()
+        offs_b = codec.block_offsets[: api.block_count(n) + 1].cpu().numpy()
+        bst_parity = "not checked (no CPU baseline on this rank)"
+        base_b = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            # compressed size == the reference's `-b` size, shard by shard, BEFORE anything is timed
+            base_b = cpu_baseline(kind="lowent_random", mode=1)
+            bps = (base_b["shard_mib"] << 20) // 65536
+            vlen = 1
+            while ((base_b["shard_mib"] << 20) >> (7 * vlen)) > 0:
+                vlen += 1
+            checked = 0
+            for i, cb in enumerate(base_b["shard_compressed_bytes"]):
+                if (i + 1) * bps >= len(offs_b):
+                    break
+                mine = int(offs_b[(i + 1) * bps]) - int(offs_b[i * bps])
+                assert mine == cb - vlen, f"BST shard {i}: {mine} bytes here, {cb - vlen} from the reference's -b"
+                checked += 1
+            assert base_b["roundtrip_ok"]
+            bst_parity = (f"compressed size equal to the reference CPU `-b` on {checked} x {base_b['shard_mib']} MiB "
+                          f"shards before timing; byte identity at 1 GiB is asserted in tests/test_gpu_baseline_sizes.py")
+        codec.decompress(stream_b, cb_bytes, hdr, n, out)
+        codec.check_status()
+        assert torch.equal(out, data_b), "BST round trip failed"
+        tb = timed(step_bst, "k_parse_exact_global (+ k_emit + k_scan_sizes + k_gather)")
+        codec.check_status()
+        tb["c_bytes"], tb["parity"], tb["base"] = cb_bytes, bst_parity, base_b
 
     # ---- end to end through the host-buffer C-ABI (pinned host memory, copies inside)
     h_stream = torch.empty(c_bytes, dtype=torch.uint8, pin_memory=True)
@@ -326,6 +385,16 @@ def run_gpu_arm(args) -> None:
     assert got["d"].size == n and torch.equal(h_out, h_data), "e2e round trip failed"
     dt_c = e2e(e2e_comp)
     assert got["c"].size == c_bytes and torch.equal(h_comp[:c_bytes], h_stream), "e2e stream differs"
+    dt_b = None
+    if tb is not None:
+        h_data.copy_(data_b)
+        torch.cuda.synchronize(dev)
+
+        def e2e_bst():
+            got["b"] = api.compress_host(h_data.numpy(), api.MODE_BST, out=h_comp.numpy())
+
+        dt_b = e2e(e2e_bst)
+        assert got["b"].size == tb["c_bytes"] and torch.equal(h_comp[:tb["c_bytes"]].to(dev), stream_b), "e2e BST stream differs"
 
     clocks = sampler.stop() if sampler else None
     td["clocks"] = tc["clocks"] = clocks
@@ -333,6 +402,7 @@ def run_gpu_arm(args) -> None:
     # ---- aggregate over ranks
     total_u = sum_over_ranks(float(n))
     total_c = sum_over_ranks(float(c_bytes))
+    total_cb_all = sum_over_ranks(float(tb["c_bytes"])) if tb is not None else 0.0
     peak, peak_src = measured_peak()
 
     try:
@@ -384,6 +454,22 @@ def run_gpu_arm(args) -> None:
                           "round trip and the K0 index are asserted before timing",
             },
         }
+        if tb is not None:
+            total_cb = total_cb_all
+            line["bst"] = {
+                "workload": f"{args.gib:g} GiB per GPU, 1 MiB segments alternating low-entropy / random (BASELINE "
+                            f"configs[3]), exact-key (BST) compression",
+                "value": total_u * args.steps / (tb["total_ms"] * 1e-3) / 1e9, "unit": "GB/s",
+                "ms_per_step": tb["total_ms"] / args.steps, "ratio": total_u / total_cb,
+                "roofline": roofline(tb, float(n + tb["c_bytes"])),
+                "e2e": {"value": total_u * e2e_steps / dt_b / 1e9, "unit": "GB/s", "h2d_bytes_per_step": n,
+                        "d2h_bytes_per_step": tb["c_bytes"], "api": "snappy_b200_compress_host (MODE_BST)"},
+                "gpu_launches": tb["launches"], "parity": tb["parity"],
+            }
+            if tb["base"] is not None:
+                b = tb["base"]
+                line["bst"]["cpu_baseline"] = {"value": b["compress_value"], "unit": "GB/s", "cores": b["cores"],
+                                               "kind": b["kind"], "sample": b["sample"], "ratio": b["ratio"]}
         if base is not None:
             line["cpu_baseline"] = base
         print(json.dumps(line), flush=True)
@@ -400,6 +486,7 @@ def main():
     ap.add_argument("--gib", type=float, default=1.0, help="corpus size per GPU in GiB")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bst", action="store_true", help="skip the configs[3] (BST path) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

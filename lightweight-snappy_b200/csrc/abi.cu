@@ -88,6 +88,7 @@ static int status_to_error(uint32_t st)
 }
 
 int fail_msg(int code, const char *msg) { return fail(code, "%s", msg); }
+void clear_error() { g_err[0] = 0; } // every public entry point starts clean: a stale message is never reported twice
 int cuda_fail_msg(cudaError_t e, const char *what) { return cuda_fail(e, what); }
 int status_error(uint32_t st) { return status_to_error(st); }
 size_t compress_workspace_bytes_internal(uint64_t n_bytes) { return compress_ws_bytes(n_bytes); }
@@ -182,6 +183,7 @@ int snappy_b200_compress_device(const uint8_t *d_in, uint64_t n_bytes, int mode,
                                 uint64_t *d_out_bytes, uint64_t *d_block_offsets, uint32_t *d_status,
                                 void *d_workspace, size_t workspace_bytes, void *stream)
 {
+    clear_error();
     if (mode != SNAPPY_B200_MODE_HASH && mode != SNAPPY_B200_MODE_BST)
         return fail(SNAPPY_B200_ERR_ARG, "unknown mode %d", mode);
     if (!d_out_bytes || !d_status || (n_bytes && (!d_in || !d_out || !d_workspace)))
@@ -216,6 +218,7 @@ int snappy_b200_compress_device(const uint8_t *d_in, uint64_t n_bytes, int mode,
 int snappy_b200_decompress_device_indexed(const uint8_t *d_stream, const uint64_t *d_block_offsets, uint64_t n_blocks,
                                           uint64_t total_out, uint8_t *d_out, uint32_t *d_status, void *stream)
 {
+    clear_error();
     if (!d_status || (n_blocks && (!d_stream || !d_block_offsets || !d_out)))
         return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
     if (n_blocks != (total_out + kBlock - 1) / kBlock)
@@ -235,6 +238,7 @@ int snappy_b200_index_device(const uint8_t *d_stream, uint64_t stream_bytes, uin
                              uint64_t *d_block_offsets, uint32_t *d_status, void *d_workspace, size_t workspace_bytes,
                              void *stream)
 {
+    clear_error();
     if (!d_stream || !d_block_offsets || !d_status || !d_workspace)
         return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
     if (body_offset > stream_bytes || stream_bytes >= (1ull << 40))
@@ -254,6 +258,7 @@ int snappy_b200_decode_segments_device(const uint8_t *d_stream, uint64_t stream_
                                        uint64_t total_out, uint8_t *d_out, const uint64_t *d_block_offsets,
                                        uint32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream)
 {
+    clear_error();
     if (!d_stream || !d_block_offsets || !d_status || !d_workspace || (!d_out && total_out))
         return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
     if (workspace_bytes < index_workspace_bytes(stream_bytes))

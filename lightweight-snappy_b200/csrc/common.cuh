@@ -34,6 +34,19 @@ __device__ __forceinline__ uint32_t ld_be32(const uint8_t *__restrict__ base, ui
     return bswap32(ld_le32(base, pos, last_word));
 }
 
+// Little-endian 32 bits at an arbitrarily aligned address; the aligned words touched are
+// clamped to `last_word`, the last aligned word that still holds a byte of the stream.
+__device__ __forceinline__ uint32_t ld_le32_any(const uint8_t *__restrict__ p, const uint32_t *__restrict__ last_word)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+    const uint32_t *w1 = w0 + 1;
+    w0 = w0 > last_word ? last_word : w0;
+    w1 = w1 > last_word ? last_word : w1;
+    return __funnelshift_r(__ldg(w0), __ldg(w1), (uint32_t)(a & 3u) * 8u);
+}
+
+
 // ---- cooperative byte copy, global -> global, any alignment -------------------------------
 cudaError_t peek_u32(uint32_t *h_pinned_dst, const void *d_src, uint32_t n_u32, cudaStream_t st); // abi.cu
 uint32_t *thread_pinned_scratch();                                                                // abi.cu
@@ -57,8 +70,8 @@ __device__ __forceinline__ void coop_copy_ro(uint8_t *__restrict__ dst, const ui
         return;
     }
     const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
-    if (tid < head)
-        dst[tid] = __ldg(src + tid);
+    for (uint32_t i = tid; i < head; i += nt)
+        dst[i] = __ldg(src + i);
     const uint32_t nchunk = (len - head) >> 4;
     const uint8_t *s0 = src + head;
     const uint32_t sa = (uint32_t)(reinterpret_cast<uintptr_t>(s0) & 3u);

@@ -40,6 +40,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace sb200 {
@@ -754,7 +756,8 @@ cudaError_t launch_compress(const uint8_t *d_in, uint64_t n_bytes, int mode, uin
     const uint64_t chains = std::min<uint64_t>(nb, (uint64_t)n_sm * 32); // one-warp CTAs: 32 per SM
     const uint64_t area = nb * (uint64_t)kSlot - 256;
     uint32_t *counters = reinterpret_cast<uint32_t *>(d_scratch + area);
-    const bool smem_tables = getenv("SNAPPY_B200_SMEM_TABLES") != nullptr; // the measured alternative
+    // the measured alternative; read per call: the test suite flips it between calls
+    const bool smem_tables = getenv("SNAPPY_B200_SMEM_TABLES") != nullptr;
     cudaError_t e = smem_tables ? cudaSuccess : cudaMemsetAsync(counters, 0, 16, st);
     if (e != cudaSuccess)
         return e;
@@ -767,16 +770,16 @@ cudaError_t launch_compress(const uint8_t *d_in, uint64_t n_bytes, int mode, uin
     } else {
         // exact mode: 8 Ki slots (16 KiB), then 64 Ki slots (128 KiB) for the blocks that outgrow them
         // (> 6144 distinct keys: text)
-        static bool attr_done = false;
-        if (!attr_done) {
+        // (the opt-in to > 48 KiB of dynamic shared memory is per device: once per device, thread-safe)
+        static std::once_flag attr_once[64];
+        std::call_once(attr_once[dev & 63], [&] {
             e = cudaFuncSetAttribute(k_parse<1, 15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 15) * 2);
-            if (e != cudaSuccess)
-                return e;
-            e = cudaFuncSetAttribute(k_parse<1, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 16) * 2);
-            if (e != cudaSuccess)
-                return e;
-            attr_done = true;
-        }
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(k_parse<1, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (1 << 16) * 2);
+        });
+        if (e != cudaSuccess)
+            return e;
         if (smem_tables)
             k_parse<1, 13, false><<<grid, cta, (1 << 13) * 2, st>>>(d_in, n_bytes, d_recs, d_nrec, 0);
         else

@@ -38,56 +38,6 @@ namespace sb200 {
 constexpr uint32_t kLongLiteral = 64;
 constexpr uint32_t kSegBytes = 128; // K0 segment size (csrc/index.cu)
 
-// Little-endian 32 bits at an arbitrarily aligned address; the aligned words touched are
-// clamped to `last_word`, the last aligned word that still holds a byte of the stream.
-__device__ __forceinline__ uint32_t ld_le32_any(const uint8_t *__restrict__ p, const uint32_t *__restrict__ last_word)
-{
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
-    const uint32_t *w1 = w0 + 1;
-    w0 = w0 > last_word ? last_word : w0;
-    w1 = w1 > last_word ? last_word : w1;
-    return __funnelshift_r(__ldg(w0), __ldg(w1), (uint32_t)(a & 3u) * 8u);
-}
-
-
-// Decodes the element whose first 4 stream bytes are v and whose tag sits at stream position pos.
-__device__ __forceinline__ Header decode_header(uint32_t v, uint32_t pos)
-{
-    Header h;
-    const uint32_t tag = v & 0xffu;
-    const uint32_t type = tag & 3u;
-    h.slow = false;
-    h.is_lit = type == 0;
-    if (type == 0) {
-        const uint32_t m = tag >> 2;
-        if (m < 60) {
-            h.hdr = 1;
-            h.len = m + 1;
-        } else {
-            const uint32_t k = m - 59; // 1..4 length bytes
-            h.hdr = 1 + k;
-            h.slow = k == 4;
-            h.len = ((v >> 8) & (0xffffffu >> (8 * (3 - min(k, 3u))))) + 1;
-        }
-        h.info = pos + h.hdr;
-    } else if (type == 1) {
-        h.hdr = 2;
-        h.len = ((tag >> 2) & 7u) + 4;
-        h.info = ((tag >> 5) << 8) | ((v >> 8) & 0xffu);
-    } else if (type == 2) {
-        h.hdr = 3;
-        h.len = (tag >> 2) + 1;
-        h.info = (v >> 8) & 0xffffu;
-    } else {
-        h.hdr = 5;
-        h.len = (tag >> 2) + 1;
-        h.info = 0;
-        h.slow = true;
-    }
-    return h;
-}
-
 // One element, handled by the whole warp (warp-uniform arguments): long literals, copy-4,
 // literals with a 4-byte length.  `in` + ip is the tag, lim the end of the compressed block.
 // Returns an error status or 0; advances ip / op.
@@ -579,9 +529,13 @@ cudaError_t launch_decode(const uint8_t *d_stream, const uint64_t *d_offsets, ui
 cudaError_t launch_decode_tile(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, const uint64_t *, uint64_t,
                                uint64_t, uint8_t *, uint32_t *, uint64_t, cudaStream_t, uint64_t *); // decode_tile.cu
 
-// Decoder for the maps K0 leaves behind.  The tile decoder (one CTA per block, output block resident in
-// shared memory) is the product path; SNAPPY_B200_DECODER=seg selects the warp-per-block decoder that
-// writes straight to global memory (kept for A/B measurements).
+cudaError_t launch_decode_win(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, uint64_t, uint64_t, uint8_t *,
+                              uint32_t *, uint64_t, cudaStream_t, uint64_t *); // decode_win.cu
+
+// Decoder for the maps K0 leaves behind.  The window decoder (decode_win.cu: a sub-warp group per block,
+// sliding output window in shared memory) is the product path.  For A/B measurements
+// SNAPPY_B200_DECODER=tile selects the one-CTA-per-block decoder with the whole 64 KiB block in shared
+// memory (decode_tile.cu) and =seg the round-1 warp-per-block decoder that writes straight to global memory.
 cudaError_t launch_decode_seg(const uint8_t *d_stream, uint64_t body_offset, const uint64_t *d_offsets,
                               const uint4 *d_starts, const uint64_t *d_outoff, uint64_t n_blocks, uint64_t total_out,
                               uint8_t *d_out, uint32_t *d_status, uint64_t blk_base, cudaStream_t st,
@@ -591,13 +545,16 @@ cudaError_t launch_decode_seg(const uint8_t *d_stream, uint64_t body_offset, con
         return cudaSuccess;
     if (n_blocks > 0x7fffffffull)
         return cudaErrorInvalidValue;
-    static const bool use_seg = [] {
+    static const char which = [] {
         const char *v = getenv("SNAPPY_B200_DECODER");
-        return v && v[0] == 's';
+        return v ? v[0] : 'w';
     }();
-    if (!use_seg)
+    if (which == 't')
         return launch_decode_tile(d_stream, body_offset, d_offsets, d_starts, d_outoff, n_blocks, total_out, d_out,
                                   d_status, blk_base, st, launches);
+    if (which != 's')
+        return launch_decode_win(d_stream, body_offset, d_offsets, d_starts, n_blocks, total_out, d_out, d_status,
+                                 blk_base, st, launches);
     // two blocks (warps) per CTA and a 48-register cap: 40 warps per SM instead of the 32 that one-warp
     // CTAs allow (measured: 64 registers / 32 warps 6.92, 48 / 40 6.72, 40 / 48 6.84 ms per GiB, K0 included)
     k_decode_seg<20><<<(unsigned)((n_blocks + 1) / 2), 64, 0, st>>>(d_stream, body_offset, d_offsets, d_starts, total_out,

@@ -14,7 +14,14 @@
 #include "snappy_decompression.h"
 #include "varint.h"
 
+namespace sb200 {
+int fail_msg(int code, const char *msg); // abi.cu: records the thread's last error
+void clear_error();
+} // namespace sb200
+
 namespace {
+
+int io_fail(const char *what) { return sb200::fail_msg(SNAPPY_B200_ERR_IO, what); }
 
 // A growable byte buffer in page-locked host memory (plain malloc when no device is usable, so
 // that error paths still work): what the reference's Buffer / IO_utils allocations become.
@@ -84,36 +91,37 @@ const char kIndexMagic[8] = {'S', 'N', 'P', 'I', 'D', 'X', '1', 0};
 int compress_file(FILE *in, unsigned long long declared, FILE *out, int mode, FILE *index_out = nullptr)
 {
     PinnedBuf data, stream;
-    if (!in || !out || !read_all(in, declared, data))
-        return SNAPPY_B200_ERR_IO;
+    sb200::clear_error();
+    if (!in || !out)
+        return io_fail("null FILE*");
+    if (!read_all(in, declared, data))
+        return io_fail("reading the input failed (read error or out of host memory)");
     if (data.empty())
         return SNAPPY_B200_OK; // reference: empty input -> empty output
     if (!stream.reserve(snappy_b200_max_compressed_bytes(data.size())))
-        return SNAPPY_B200_ERR_IO;
+        return io_fail("out of host memory for the compressed stream");
     uint64_t n = 0;
     const uint64_t nb = snappy_b200_block_count(data.size());
     uint64_t *offsets = index_out ? static_cast<uint64_t *>(malloc((nb + 1) * 8)) : nullptr;
     if (index_out && !offsets)
-        return SNAPPY_B200_ERR_IO;
+        return io_fail("out of host memory for the block index");
     struct Free {
         void *p;
         ~Free() { free(p); }
     } free_offsets{offsets};
     const int rc =
         snappy_b200_compress_host_indexed(data.data(), data.size(), mode, stream.data(), stream.cap, &n, offsets);
-    if (rc != SNAPPY_B200_OK) {
-        fprintf(stderr, "snappy_b200: %s\n", snappy_b200_last_error());
-        return rc;
-    }
+    if (rc != SNAPPY_B200_OK)
+        return rc; // (the message is in snappy_b200_last_error())
     // The reference writes the DECLARED size into the preamble (src/snappy_compression.c:417)
     // and then whatever the file really held; keep that even when the two disagree.
     unsigned char hdr[10];
     const unsigned hdr_real = parse_to_varint(data.size(), hdr);
     const unsigned hdr_decl = parse_to_varint(declared, hdr);
     if (fwrite(hdr, 1, hdr_decl, out) != hdr_decl)
-        return SNAPPY_B200_ERR_IO;
+        return io_fail("short write of the compressed stream");
     if (fwrite(stream.data() + hdr_real, 1, n - hdr_real, out) != n - hdr_real)
-        return SNAPPY_B200_ERR_IO;
+        return io_fail("short write of the compressed stream");
     if (index_out) {
         // offsets as they are in the file just written (the declared-size preamble may be longer or shorter)
         for (uint64_t b = 0; b <= nb; ++b)
@@ -121,7 +129,7 @@ int compress_file(FILE *in, unsigned long long declared, FILE *out, int mode, FI
         const uint64_t head[2] = {data.size(), nb};
         if (fwrite(kIndexMagic, 1, 8, index_out) != 8 || fwrite(head, 8, 2, index_out) != 2 ||
             fwrite(offsets, 8, nb + 1, index_out) != nb + 1)
-            return SNAPPY_B200_ERR_IO;
+            return io_fail("short write of the block index");
     }
     return SNAPPY_B200_OK;
 }
@@ -138,34 +146,30 @@ int snappy_b200_compress_file_indexed(FILE *in, unsigned long long input_size, i
 int snappy_b200_decompress_file_indexed(FILE *in, FILE *index_in, FILE *out)
 {
     PinnedBuf stream, data;
+    sb200::clear_error();
     if (!in || !index_in || !out || !read_all(in, 0, stream))
-        return SNAPPY_B200_ERR_IO;
+        return io_fail("reading the compressed stream failed");
     char magic[8];
     uint64_t head[2];
     if (fread(magic, 1, 8, index_in) != 8 || memcmp(magic, kIndexMagic, 8) != 0 || fread(head, 8, 2, index_in) != 2 ||
         head[1] != snappy_b200_block_count(head[0]) || head[1] >= (1ull << 31)) {
-        fprintf(stderr, "snappy_b200: not a block index file\n");
-        return SNAPPY_B200_ERR_CORRUPT;
+        return sb200::fail_msg(SNAPPY_B200_ERR_CORRUPT, "not a block index file");
     }
     uint64_t *offsets = static_cast<uint64_t *>(malloc((head[1] + 1) * 8));
     if (!offsets)
-        return SNAPPY_B200_ERR_IO;
+        return io_fail("out of host memory for the block index");
     int rc = SNAPPY_B200_OK;
-    if (fread(offsets, 8, head[1] + 1, index_in) != head[1] + 1) {
-        fprintf(stderr, "snappy_b200: truncated block index file\n");
-        rc = SNAPPY_B200_ERR_CORRUPT;
-    }
+    if (fread(offsets, 8, head[1] + 1, index_in) != head[1] + 1)
+        rc = sb200::fail_msg(SNAPPY_B200_ERR_CORRUPT, "truncated block index file");
     uint64_t n = 0;
     if (rc == SNAPPY_B200_OK && head[0] && !data.reserve(head[0]))
-        rc = SNAPPY_B200_ERR_IO;
+        rc = io_fail("out of host memory for the output");
     if (rc == SNAPPY_B200_OK && head[0]) {
         rc = snappy_b200_decompress_host_indexed(stream.data(), stream.size(), offsets, head[1], data.data(), data.cap, &n);
         if (rc == SNAPPY_B200_OK && n != head[0])
-            rc = SNAPPY_B200_ERR_CORRUPT;
+            rc = sb200::fail_msg(SNAPPY_B200_ERR_CORRUPT, "the index file declares another length than the stream");
         if (rc == SNAPPY_B200_OK && fwrite(data.data(), 1, n, out) != n)
-            rc = SNAPPY_B200_ERR_IO;
-        else if (rc != SNAPPY_B200_OK)
-            fprintf(stderr, "snappy_b200: %s\n", snappy_b200_last_error());
+            rc = io_fail("short write of the output");
     }
     free(offsets);
     return rc;
@@ -184,20 +188,19 @@ int snappy_compress_bst(FILE *file_input, unsigned long long input_size, FILE *f
 int snappy_decompress(FILE *file_input, FILE *file_decompressed)
 {
     PinnedBuf stream, out;
+    sb200::clear_error();
     if (!file_input || !file_decompressed || !read_all(file_input, 0, stream))
-        return SNAPPY_B200_ERR_IO;
+        return io_fail("reading the compressed stream failed");
     uint64_t total = 0;
     int rc = snappy_b200_uncompressed_length(stream.data(), stream.size(), &total);
     if (rc == SNAPPY_B200_OK && total) {
         if (!out.reserve(total))
-            return SNAPPY_B200_ERR_IO;
+            return io_fail("out of host memory for the output");
         uint64_t n = 0;
         rc = snappy_b200_decompress_host(stream.data(), stream.size(), out.data(), out.cap, &n);
         if (rc == SNAPPY_B200_OK && fwrite(out.data(), 1, n, file_decompressed) != n)
-            rc = SNAPPY_B200_ERR_IO;
+            rc = io_fail("short write of the output");
     }
-    if (rc != SNAPPY_B200_OK && rc != SNAPPY_B200_ERR_IO)
-        fprintf(stderr, "snappy_b200: %s\n", snappy_b200_last_error());
     return rc;
 }
 

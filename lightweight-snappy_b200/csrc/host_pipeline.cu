@@ -33,6 +33,7 @@
 
 namespace sb200 {
 int fail_msg(int code, const char *msg);
+void clear_error();
 int cuda_fail_msg(cudaError_t e, const char *what);
 int status_error(uint32_t st);
 size_t compress_workspace_bytes_internal(uint64_t n_bytes);
@@ -348,6 +349,7 @@ int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *
 int snappy_b200_compress_host_indexed(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
                                       uint64_t *out_bytes, uint64_t *block_offsets)
 {
+    clear_error();
     if (!out_bytes || (n_bytes && (!in || !out)))
         return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
     if (mode != SNAPPY_B200_MODE_HASH && mode != SNAPPY_B200_MODE_BST)
@@ -457,6 +459,7 @@ int snappy_b200_compress_host_indexed(const void *in, uint64_t n_bytes, int mode
 
 int snappy_b200_uncompressed_length(const void *stream, uint64_t stream_bytes, uint64_t *n_bytes)
 {
+    clear_error();
     if (!n_bytes)
         return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
     *n_bytes = 0;
@@ -470,6 +473,7 @@ int snappy_b200_uncompressed_length(const void *stream, uint64_t stream_bytes, u
 int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void *out, uint64_t out_capacity,
                                 uint64_t *out_bytes)
 {
+    clear_error();
     if (!out_bytes || (stream_bytes && !stream))
         return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
     *out_bytes = 0;
@@ -582,6 +586,7 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
 int snappy_b200_decompress_host_indexed(const void *stream, uint64_t stream_bytes, const uint64_t *block_offsets,
                                         uint64_t n_blocks, void *out, uint64_t out_capacity, uint64_t *out_bytes)
 {
+    clear_error();
     if (!out_bytes || (stream_bytes && !stream) || !block_offsets)
         return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
     *out_bytes = 0;
@@ -672,6 +677,7 @@ int snappy_b200_decompress_device(const uint8_t *d_stream, uint64_t stream_bytes
                                   uint64_t total_out, uint8_t *d_out, uint64_t *d_block_offsets, uint32_t *d_status,
                                   void *d_workspace, size_t workspace_bytes, void *stream)
 {
+    clear_error();
     if (!d_stream || !d_status || !d_workspace || (!d_out && total_out))
         return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
     if (body_offset > stream_bytes || stream_bytes >= (1ull << 40))

@@ -40,6 +40,8 @@
 //                      each element that starts a 64 KiB output block; elements that straddle
 //                      a block boundary (legal raw Snappy, never produced by this framing) are
 //                      reported as SNAPPY_B200_ST_FRAMING.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace sb200 {
@@ -822,7 +824,7 @@ const uint4 *index_starts(void *d_ws, uint64_t stream_bytes) { return carve(d_ws
 // Output offset of the first element that starts in each segment (exclusive scan of the segment output lengths).
 const uint64_t *index_outoff(void *d_ws, uint64_t stream_bytes) { return carve(d_ws, stream_bytes).outoff; }
 
-static uint64_t g_last_rounds = 0;
+static std::atomic<uint64_t> g_last_rounds{0}; // diagnostic only (last call on any thread)
 uint64_t index_last_rounds() { return g_last_rounds; }
 
 // Synchronises the stream between relaxation rounds (it has to read the "changed" flag).

@@ -16,6 +16,43 @@ struct Header {
     bool slow; // header does not fit in the 4 bytes of v
 };
 
+// Decodes the element whose first 4 stream bytes are v and whose tag sits at stream position pos.
+__device__ __forceinline__ Header decode_header(uint32_t v, uint32_t pos)
+{
+    Header h;
+    const uint32_t tag = v & 0xffu;
+    const uint32_t type = tag & 3u;
+    h.slow = false;
+    h.is_lit = type == 0;
+    if (type == 0) {
+        const uint32_t m = tag >> 2;
+        if (m < 60) {
+            h.hdr = 1;
+            h.len = m + 1;
+        } else {
+            const uint32_t k = m - 59; // 1..4 length bytes
+            h.hdr = 1 + k;
+            h.slow = k == 4;
+            h.len = ((v >> 8) & (0xffffffu >> (8 * (3 - min(k, 3u))))) + 1;
+        }
+        h.info = pos + h.hdr;
+    } else if (type == 1) {
+        h.hdr = 2;
+        h.len = ((tag >> 2) & 7u) + 4;
+        h.info = ((tag >> 5) << 8) | ((v >> 8) & 0xffu);
+    } else if (type == 2) {
+        h.hdr = 3;
+        h.len = (tag >> 2) + 1;
+        h.info = (v >> 8) & 0xffffu;
+    } else {
+        h.hdr = 5;
+        h.len = (tag >> 2) + 1;
+        h.info = 0;
+        h.slow = true;
+    }
+    return h;
+}
+
 // Tag byte -> header facts, looked up instead of branched over:
 //   bits 0-2 header bytes, bits 3-9 output length when the tag alone gives it (0: a literal whose
 //   length follows in 1..4 bytes), bit 10 literal, bit 11 header longer than 4 bytes (copy-4, 4-byte

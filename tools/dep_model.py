@@ -110,3 +110,46 @@ if __name__ == "__main__":
     for kind, seg in (("text", 0), ("lowent", 1), ("random", 2)):
         d = cp.make_segment(kind, seg).numpy()[:65536].tobytes()
         analyse(kind, d)
+
+
+def window_rounds(els, gw, wkeep):
+    """Rounds of in-order multi-round resolution when the elements are taken gw at a time by one
+    sub-warp group; literals and copies that reach further back than `wkeep` are ready at once."""
+    total = 0; passes = 0
+    i = 0
+    n = len(els)
+    while i < n:
+        if els[i][0] == 0 and els[i][3] > 64:
+            i += 1; passes += 1; total += 1; continue
+        j = i
+        while j < n and j - i < gw and not (els[j][0] == 0 and els[j][3] > 64):
+            j += 1
+        pend = [m for m in range(i, j) if els[m][0] == 1 and els[m][4] <= wkeep]
+        rounds = 1  # round 0: literals, far copies and whatever is ready
+        first = True
+        while pend:
+            hwm = els[pend[0]][2]
+            nxt = [m for m in pend if m != pend[0] and min(els[m][2] - els[m][4] + els[m][3], els[m][2]) > hwm]
+            if not first:
+                rounds += 1
+            first = False
+            pend = nxt
+        total += rounds; passes += 1
+        i = j
+    return passes, total
+
+
+def report_windows():
+    import corpus as cp
+    o = Oracle()
+    for kind, seg in (("text", 0), ("lowent", 1)):
+        d = cp.make_segment(kind, seg).numpy()[:65536].tobytes()
+        els = parse(bytes(o.compress(d, 0)))
+        for gw in (8, 16, 32):
+            p, r = window_rounds(els, gw, 3584)
+            print(f"{kind}: group width {gw}: {p} passes, {r} rounds per block ({r / p:.2f} per pass); "
+                  f"warp-level rounds per block when {32 // gw} blocks share a warp: {r * gw / 32:.0f}")
+
+
+if __name__ == "__main__":
+    report_windows()
