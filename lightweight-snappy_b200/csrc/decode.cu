@@ -254,6 +254,11 @@ __global__ void __launch_bounds__(64, MINB) k_decode_seg(const uint8_t *__restri
             atomicOr(status, SNAPPY_B200_ST_CORRUPT);
         return;
     }
+    {
+        const uint64_t oleft0 = total_out - blk * (uint64_t)kBlock;
+        if (one_literal_block(stream, c0, c1, oleft0 < kBlock ? (uint32_t)oleft0 : kBlock))
+            return; // k_copy_literal_blocks has moved it
+    }
     const uint32_t *last_word = reinterpret_cast<const uint32_t *>(
         reinterpret_cast<uintptr_t>(stream + stream_bytes - 1) & ~uintptr_t(3));
     // stream positions below are relative to the first segment the block touches
@@ -532,10 +537,20 @@ cudaError_t launch_decode_tile(const uint8_t *, uint64_t, const uint64_t *, cons
 cudaError_t launch_decode_win(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, uint64_t, uint64_t, uint8_t *,
                               uint32_t *, uint64_t, cudaStream_t, uint64_t *); // decode_win.cu
 
-// Decoder for the maps K0 leaves behind.  The window decoder (decode_win.cu: a sub-warp group per block,
-// sliding output window in shared memory) is the product path.  For A/B measurements
-// SNAPPY_B200_DECODER=tile selects the one-CTA-per-block decoder with the whole 64 KiB block in shared
-// memory (decode_tile.cu) and =seg the round-1 warp-per-block decoder that writes straight to global memory.
+cudaError_t launch_decode_lane(const uint8_t *, uint64_t, const uint64_t *, uint64_t, uint64_t, uint8_t *, uint32_t *,
+                               uint64_t, bool, cudaStream_t, uint64_t *); // decode_lane.cu
+
+cudaError_t launch_copy_literal_blocks(const uint8_t *, uint64_t, const uint64_t *, uint64_t, uint64_t, uint8_t *,
+                                       const uint32_t *, cudaStream_t, uint64_t *); // decode_lane.cu
+
+// Decoder for the maps K0 leaves behind.  The product path is the warp-per-block, segment-driven decoder
+// above (k_decode_seg) preceded by k_copy_literal_blocks, which moves the blocks that are a single literal
+// (incompressible data) with plain 16-byte vector copies.  Three other designs were built and measured in
+// round 2 and lost (1 GiB mixed corpus: seg 4.1 ms; profiles/r02_*): SNAPPY_B200_DECODER=tile selects the
+// one-CTA-per-block decoder with the whole 64 KiB block in shared memory (decode_tile.cu, 32 ms), =win the
+// sub-warp-group-per-block decoder with a sliding shared-memory window (decode_win.cu, 9.3 ms), =lane the
+// one-lane-per-block sequential decoder (decode_lane.cu, 18.7 ms; 9.4 ms/GiB at 4 GiB).  All four are
+// bit-exact (tests/test_gpu_parity.py::test_alternative_decoders).
 cudaError_t launch_decode_seg(const uint8_t *d_stream, uint64_t body_offset, const uint64_t *d_offsets,
                               const uint4 *d_starts, const uint64_t *d_outoff, uint64_t n_blocks, uint64_t total_out,
                               uint8_t *d_out, uint32_t *d_status, uint64_t blk_base, cudaStream_t st,
@@ -547,14 +562,22 @@ cudaError_t launch_decode_seg(const uint8_t *d_stream, uint64_t body_offset, con
         return cudaErrorInvalidValue;
     static const char which = [] {
         const char *v = getenv("SNAPPY_B200_DECODER");
-        return v ? v[0] : 'w';
+        return v ? v[0] : 's';
     }();
+    if (which == 'l')
+        return launch_decode_lane(d_stream, body_offset, d_offsets, n_blocks, total_out, d_out, d_status, blk_base, true,
+                                  st, launches);
     if (which == 't')
         return launch_decode_tile(d_stream, body_offset, d_offsets, d_starts, d_outoff, n_blocks, total_out, d_out,
                                   d_status, blk_base, st, launches);
-    if (which != 's')
+
+    if (which == 'w')
         return launch_decode_win(d_stream, body_offset, d_offsets, d_starts, n_blocks, total_out, d_out, d_status,
                                  blk_base, st, launches);
+    cudaError_t e = launch_copy_literal_blocks(d_stream, body_offset, d_offsets, n_blocks, total_out, d_out, d_status, st,
+                                               launches);
+    if (e != cudaSuccess)
+        return e;
     // two blocks (warps) per CTA and a 48-register cap: 40 warps per SM instead of the 32 that one-warp
     // CTAs allow (measured: 64 registers / 32 warps 6.92, 48 / 40 6.72, 40 / 48 6.84 ms per GiB, K0 included)
     k_decode_seg<20><<<(unsigned)((n_blocks + 1) / 2), 64, 0, st>>>(d_stream, body_offset, d_offsets, d_starts, total_out,

@@ -92,4 +92,20 @@ __device__ __forceinline__ Header decode_header_lut(const uint16_t *__restrict__
     return h;
 }
 
+// Is the block [c0, c1) of the stream exactly one literal of olen bytes (incompressible data)?
+__device__ __forceinline__ bool one_literal_block(const uint8_t *__restrict__ stream, uint64_t c0, uint64_t c1, uint32_t olen)
+{
+    const uint8_t *p = stream + c0;
+    const uint32_t tag = __ldg(p);
+    if ((tag & 3u) != 0 || (tag >> 2) < 60u)
+        return false;
+    const uint32_t k = (tag >> 2) - 59u; // length bytes
+    if (c1 - c0 <= 1 + k)
+        return false;
+    uint64_t raw = 0;
+    for (uint32_t i = 0; i < k; ++i)
+        raw |= (uint64_t)__ldg(p + 1 + i) << (8u * i);
+    return raw + 1 == olen && c1 - c0 == 1ull + k + olen;
+}
+
 } // namespace sb200

@@ -350,3 +350,41 @@ def test_cli_side_index(tmp_path):
     assert idx[:8] == b"SNPIDX1\0" and len(idx) == 24 + 8 * (api.block_count(data.size) + 1)
     subprocess.run([api.CLI_PATH, "-d", "-i", str(comp), str(back)], check=True, timeout=300)
     assert back.read_bytes() == data.tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["seg", "tile", "win", "lane"])
+def test_alternative_decoders(which, tmp_path):
+    """The four block decoders (SNAPPY_B200_DECODER, read once per process: csrc/decode.cu) must all be
+    bit-exact against the oracle decoder: the product one (seg) and the three measured-and-rejected
+    designs kept for A/B (tile, win, lane)."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, os, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import oracle_lib, streamgen, datasets
+from lightweight_snappy_b200 import api
+o = oracle_lib.Oracle()
+for seed, (total, style) in enumerate([(1, "mixed"), (4095, "copies"), (65537, "copies"), (300001, "bigliteral"), (1 << 20, "mixed"), (2 << 20, "copies")]):
+    stream, want = streamgen.make_stream(2000 + seed, total, style)
+    assert np.array_equal(o.decompress(stream), want)
+    got = api.snappy_decompress(stream)
+    assert got.size == want.size and np.array_equal(got, want), (seed, total, style)
+for spec in ("corpus:mixed:0:0:7000000", "corpus:lowent:1:0:3000001", "rep:0:200000", "period:3:3:140000", "corpus:random:2:0:200000"):
+    data = datasets.gen(spec)
+    s = o.compress(data, 0)
+    got = api.snappy_decompress(s)
+    assert got.size == data.size and np.array_equal(got, data), spec
+for bad in (b"\x08\x0cabcd" + bytes([(3 << 2) | 2, 9, 0]), b"\x08\x0cab", b"\x04\x0cabcd\x0cabcd", b"\x20\x0cabcd"):
+    try:
+        api.snappy_decompress(np.frombuffer(bad, np.uint8))
+    except api.SnappyError:
+        continue
+    raise AssertionError("malformed stream accepted")
+print("OK")
+"""
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    env = dict(os.environ, SNAPPY_B200_DECODER=which)
+    r = subprocess.run([sys.executable, "-c", code % (root, root)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
