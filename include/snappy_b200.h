@@ -59,7 +59,7 @@ extern "C" {
 #define SNAPPY_B200_ST_CAPACITY 1u
 #define SNAPPY_B200_ST_CORRUPT 2u
 #define SNAPPY_B200_ST_FRAMING 4u
-#define SNAPPY_B200_ST_UNRESOLVED 8u /* internal: the stream index did not converge */
+#define SNAPPY_B200_ST_UNRESOLVED 8u /* the element chain did not resolve within the relaxation rounds run */
 
 /* Message of the last failing call on this thread (never NULL). */
 const char *snappy_b200_last_error(void);
@@ -125,6 +125,19 @@ size_t snappy_b200_decompress_workspace_bytes(uint64_t stream_bytes, uint64_t to
 int snappy_b200_decompress_device(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
                                   uint64_t total_out, uint8_t *d_out, uint64_t *d_block_offsets,
                                   uint32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* The same decode as a purely ASYNCHRONOUS call: K0 runs a fixed batch of max_rounds (<= 64; 0 = 64)
+ * relaxation rounds that end themselves on the device as soon as the chain is resolved, then the block
+ * decode follows on the same stream.  Nothing is read back, nothing synchronises, no lock is taken and
+ * nothing is allocated, so the call may be captured into a CUDA graph and replayed.  If the stream needs
+ * more rounds than were enqueued (measured: text 5, low-entropy 4, mixed 10, random 38) *d_status gets
+ * SNAPPY_B200_ST_UNRESOLVED and nothing is decoded: use snappy_b200_decompress_device for such input.
+ * d_block_offsets (optional) as above.  *d_status is OR-ed into; the caller zeroes it.              */
+size_t snappy_b200_decompress_async_workspace_bytes(uint64_t stream_bytes, uint64_t total_out);
+int snappy_b200_decompress_device_async(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
+                                        uint64_t total_out, uint8_t *d_out, uint64_t *d_block_offsets,
+                                        uint32_t *d_status, void *d_workspace, size_t workspace_bytes,
+                                        unsigned max_rounds, void *stream);
 
 /* ---------------------------------------------------------------- 2. host-buffer API
  * Synchronous.  Host pointers (pageable or pinned); staging through pinned buffers and

@@ -52,6 +52,9 @@ SIGNATURES = {
     "snappy_b200_decompress_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_uint64]),
     "snappy_b200_decompress_device": (C.c_int, [_u8p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u8p, _u8p, _u8p,
                                                 C.c_size_t, C.c_void_p]),
+    "snappy_b200_decompress_async_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_uint64]),
+    "snappy_b200_decompress_device_async": (C.c_int, [_u8p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u8p, _u8p, _u8p,
+                                                      C.c_size_t, C.c_uint, C.c_void_p]),
     "snappy_b200_compress_host": (C.c_int, [_u8p, C.c_uint64, C.c_int, _u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "snappy_b200_uncompressed_length": (C.c_int, [_u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "snappy_b200_decompress_host": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
@@ -212,7 +215,8 @@ class DeviceCodec:
         self.comp_capacity = max(int(L.snappy_b200_max_compressed_bytes(max_bytes)), 16)
         ws = max(int(L.snappy_b200_compress_workspace_bytes(max_bytes, MODE_BST)),
                  int(L.snappy_b200_index_workspace_bytes(self.comp_capacity)),
-                 int(L.snappy_b200_decompress_workspace_bytes(self.comp_capacity, max_bytes)))
+                 int(L.snappy_b200_decompress_workspace_bytes(self.comp_capacity, max_bytes)),
+                 int(L.snappy_b200_decompress_async_workspace_bytes(self.comp_capacity, max_bytes)))
         self.workspace = torch.empty(ws + 256, dtype=torch.uint8, device=self.device)
         self.stream_buf = torch.empty(self.comp_capacity + 256, dtype=torch.uint8, device=self.device)
         self.block_offsets = torch.zeros(nb + 1, dtype=torch.int64, device=self.device)
@@ -247,6 +251,18 @@ class DeviceCodec:
             stream_t.data_ptr(), stream_bytes, body_offset, total_out, out.data_ptr(), block_offsets.data_ptr(),
             self.status.data_ptr(), self.workspace.data_ptr(), self.workspace.numel(), self._stream()))
         return block_offsets
+
+    def decompress_async(self, stream_t, stream_bytes: int, body_offset: int, total_out: int, out, block_offsets=None,
+                         max_rounds: int = 64, zero_status: bool = True):
+        """Index-less decode, enqueue-only (no host synchronisation: may be captured into a CUDA graph).
+        K0 runs a fixed batch of `max_rounds` self-terminating relaxation rounds; status gets
+        ST_UNRESOLVED if the stream needed more."""
+        if zero_status:
+            self.status.zero_()
+        _check(lib().snappy_b200_decompress_device_async(
+            stream_t.data_ptr(), stream_bytes, body_offset, total_out, out.data_ptr(),
+            block_offsets.data_ptr() if block_offsets is not None else None,
+            self.status.data_ptr(), self.workspace.data_ptr(), self.workspace.numel(), max_rounds, self._stream()))
 
     def decode_segments(self, stream_t, stream_bytes: int, body_offset: int, total_out: int, out, block_offsets):
         """Second half of decompress(): needs the workspace as index() left it (status is kept)."""

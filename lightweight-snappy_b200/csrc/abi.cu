@@ -22,7 +22,7 @@ const uint4 *index_starts(void *, uint64_t);
 const uint64_t *index_outoff(void *, uint64_t);
 size_t index_workspace_bytes(uint64_t);
 cudaError_t run_index(const uint8_t *, uint64_t, uint64_t, uint64_t, uint64_t *, uint32_t *, void *, cudaStream_t,
-                      uint64_t *, bool, uint64_t);
+                      uint64_t *, bool, uint64_t, uint32_t fixed_rounds = 0);
 uint32_t host_varint_len(uint64_t);
 uint64_t index_last_rounds();
 
@@ -80,6 +80,11 @@ static int status_to_error(uint32_t st)
         return fail(SNAPPY_B200_ERR_CORRUPT, "malformed compressed stream (device status 0x%x)", st);
     if (st & SNAPPY_B200_ST_FRAMING)
         return fail(SNAPPY_B200_ERR_FRAMING, "an element straddles a 64 KiB block (device status 0x%x)", st);
+    if (st & SNAPPY_B200_ST_UNRESOLVED)
+        return fail(SNAPPY_B200_ERR_CORRUPT,
+                    "the element chain of the stream did not resolve within the relaxation rounds allowed "
+                    "(device status 0x%x): adversarial input, or max_rounds too small for the asynchronous call",
+                    st);
     if (st & SNAPPY_B200_ST_CAPACITY)
         return fail(SNAPPY_B200_ERR_CAPACITY, "output buffer too small (device status 0x%x)", st);
     if (st)
@@ -270,6 +275,46 @@ int snappy_b200_decode_segments_device(const uint8_t *d_stream, uint64_t stream_
     g_launches += launches;
     if (e != cudaSuccess)
         return cuda_fail(e, "decode launch");
+    return SNAPPY_B200_OK;
+}
+
+// ---- asynchronous index-less decode: K0 with a fixed number of relaxation rounds (ended on the device)
+// followed by the block decode, all enqueued on `stream`: no host read-back, no synchronisation, no lock,
+// no allocation -- the call can be captured into a CUDA graph.
+size_t snappy_b200_decompress_async_workspace_bytes(uint64_t stream_bytes, uint64_t total_out)
+{
+    const uint64_t nb = (total_out + kBlock - 1) / kBlock;
+    return align_up(index_workspace_bytes(stream_bytes), 256) + align_up((nb + 2) * 8, 256);
+}
+
+int snappy_b200_decompress_device_async(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
+                                        uint64_t total_out, uint8_t *d_out, uint64_t *d_block_offsets, uint32_t *d_status,
+                                        void *d_workspace, size_t workspace_bytes, unsigned max_rounds, void *stream)
+{
+    clear_error();
+    if (!d_stream || !d_status || !d_workspace || (!d_out && total_out))
+        return fail(SNAPPY_B200_ERR_ARG, "null pointer argument");
+    if (body_offset > stream_bytes || stream_bytes >= (1ull << 40))
+        return fail(SNAPPY_B200_ERR_ARG, "bad stream size / body offset");
+    if (workspace_bytes < snappy_b200_decompress_async_workspace_bytes(stream_bytes, total_out))
+        return fail(SNAPPY_B200_ERR_ARG, "workspace too small (see snappy_b200_decompress_async_workspace_bytes)");
+    if (total_out == 0)
+        return SNAPPY_B200_OK;
+    const uint64_t nb = (total_out + kBlock - 1) / kBlock;
+    uint64_t *offs = d_block_offsets
+                         ? d_block_offsets
+                         : reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(d_workspace) +
+                                                        align_up(index_workspace_bytes(stream_bytes), 256));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint64_t launches = 0;
+    cudaError_t e = run_index(d_stream, stream_bytes, body_offset, total_out, offs, d_status, d_workspace, st, &launches,
+                              false, 0, max_rounds ? max_rounds : 64u);
+    if (e == cudaSuccess)
+        e = launch_decode_seg(d_stream, body_offset, offs, index_starts(d_workspace, stream_bytes),
+                              index_outoff(d_workspace, stream_bytes), nb, total_out, d_out, d_status, 0, st, &launches);
+    g_launches += launches;
+    if (e != cudaSuccess)
+        return cuda_fail(e, "asynchronous decompress launch");
     return SNAPPY_B200_OK;
 }
 

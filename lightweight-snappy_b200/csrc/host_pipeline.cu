@@ -42,7 +42,7 @@ cudaError_t compress_chunk(const uint8_t *, uint64_t, uint64_t, int, uint8_t *, 
                            cudaStream_t);
 size_t index_workspace_bytes(uint64_t);
 cudaError_t run_index(const uint8_t *, uint64_t, uint64_t, uint64_t, uint64_t *, uint32_t *, void *, cudaStream_t,
-                      uint64_t *, bool, uint64_t);
+                      uint64_t *, bool, uint64_t, uint32_t fixed_rounds = 0);
 const uint4 *index_starts(void *, uint64_t);
 const uint64_t *index_total(void *, uint64_t);
 const uint64_t *compress_chunk_offsets(void *, uint64_t);

@@ -40,6 +40,7 @@
 //                      each element that starts a 64 KiB output block; elements that straddle
 //                      a block boundary (legal raw Snappy, never produced by this framing) are
 //                      reported as SNAPPY_B200_ST_FRAMING.
+#include <algorithm>
 #include <atomic>
 
 #include "common.cuh"
@@ -347,8 +348,11 @@ __device__ __forceinline__ bool is_max_literal(const uint8_t *__restrict__ body,
 __global__ void __launch_bounds__(128) k_group_scatter(const uint8_t *__restrict__ body, uint64_t body_len,
                                                        uint64_t ngroup, const uint32_t *__restrict__ g_entry,
                                                        const uint64_t *__restrict__ g_exit,
-                                                       unsigned long long *__restrict__ g_claim)
+                                                       unsigned long long *__restrict__ g_claim,
+                                                       const uint32_t *__restrict__ prev_changed)
 {
+    if (prev_changed && *prev_changed == 0)
+        return; // the round before changed nothing: the fixed point is reached, the rest of the batch is idle
     const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (g >= ngroup)
         return;
@@ -462,9 +466,12 @@ __global__ void __launch_bounds__(kGroupCta) k_group_apply32(const uint8_t *__re
                                                              uint64_t *__restrict__ g_exit,
                                                              uint64_t *__restrict__ g_vis,
                                                              unsigned long long *__restrict__ g_claim,
-                                                             uint32_t *__restrict__ changed)
+                                                             uint32_t *__restrict__ changed,
+                                                             const uint32_t *__restrict__ prev_changed)
 {
     __shared__ GroupStage stage[kGroupCta / 32];
+    if (prev_changed && *prev_changed == 0)
+        return; // fixed point reached earlier in this batch
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t n_warps = (uint64_t)gridDim.x * (kGroupCta / 32);
     const uint64_t w = blockIdx.x * (uint64_t)(kGroupCta / 32) + (threadIdx.x >> 5);
@@ -755,8 +762,12 @@ __global__ void __launch_bounds__(256) k_index_blocks(const uint8_t *__restrict_
 
 __global__ void k_index_finish(const uint64_t *__restrict__ total, uint64_t total_out, uint64_t stream_bytes,
                                uint64_t n_blocks, uint64_t *__restrict__ block_offsets, uint32_t *__restrict__ status,
-                               int open_end)
+                               int open_end, const uint32_t *__restrict__ last_changed)
 {
+    // the last relaxation round that was run still moved a group: the chain is not resolved, nothing
+    // built on it may be trusted (the decode kernels return at once on a non-zero status)
+    if (threadIdx.x == 0 && blockIdx.x == 0 && last_changed && *last_changed != 0)
+        atomicOr(status, SNAPPY_B200_ST_UNRESOLVED);
     if (threadIdx.x == 0 && blockIdx.x == 0 && !open_end) {
         block_offsets[n_blocks] = stream_bytes;
         if (*total != total_out)
@@ -834,9 +845,19 @@ const uint64_t *index_total(void *d_ws, uint64_t stream_bytes) { return carve(d_
 // open_end: the bytes are the beginning of a longer stream (the host pipeline decodes while the
 // rest is still being uploaded).  The element cut off by the end is not an error then, the
 // total is not checked, and at most n_blocks_cap block starts are recorded.
+//
+// The relaxation rounds end on the device: every round reads the "changed" flag of the round before and
+// returns at once when it is clear, so a batch of rounds can be enqueued blind.
+//   fixed_rounds == 0  adaptive: batches of 16, 48, 64, ... rounds, the flags read back after each batch
+//                      (synchronises the stream); gives up with ST_UNRESOLVED after kMaxRounds.
+//   fixed_rounds  > 0  asynchronous: exactly one batch of min(fixed_rounds, 64) rounds, no read-back, no
+//                      synchronisation (graph-capturable); ST_UNRESOLVED if its last round still moved.
+constexpr uint32_t kMaxBatch = 64;
+constexpr uint64_t kMaxRounds = 1u << 14; // an adversarial stream may need one round per group: bounded instead
+
 cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset, uint64_t total_out,
                       uint64_t *d_block_offsets, uint32_t *d_status, void *d_ws, cudaStream_t st, uint64_t *launches,
-                      bool open_end, uint64_t n_blocks_cap)
+                      bool open_end, uint64_t n_blocks_cap, uint32_t fixed_rounds)
 {
     const uint64_t n_blocks = open_end ? n_blocks_cap : (total_out + kBlock - 1) / kBlock;
     const uint64_t body_len = stream_bytes - body_offset;
@@ -848,7 +869,7 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
         if ((e = cudaMemsetAsync(w.total, 0, 8, st)) != cudaSuccess)
             return e;
         k_index_finish<<<1, 32, 0, st>>>(w.total, total_out, stream_bytes, n_blocks, d_block_offsets, d_status,
-                                         open_end);
+                                         open_end, nullptr);
         *launches += 1;
         return cudaGetLastError();
     }
@@ -861,40 +882,49 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
     k_group_init<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.g_exit, w.g_vis,
                                         w.claim);
     *launches += 2;
-    // The "did anything change" flags are only read back every few rounds (4, then 8, 16, ... 64):
-    // a round costs two short kernels, a host round trip costs more.
-    constexpr uint32_t kMaxBatch = 64;
-    const uint64_t max_rounds = ngroup + 2 + kMaxBatch;
-    if ((e = cudaMemsetAsync(w.changed, 0, 4 * kMaxBatch, st)) != cudaSuccess)
-        return e;
-    uint32_t batch = 4;
-    for (uint64_t round = 0; round < max_rounds; round += batch, batch = min(batch * 2, kMaxBatch)) {
+    const uint64_t max_rounds = std::min<uint64_t>(ngroup + 2 + kMaxBatch, kMaxRounds);
+    const uint32_t *unresolved = nullptr; // flag of the last round run, when nothing proves convergence
+    uint32_t batch = fixed_rounds ? std::min<uint32_t>(fixed_rounds, kMaxBatch) : 16;
+    for (uint64_t round = 0;;) {
+        if ((e = cudaMemsetAsync(w.changed, 0, 4 * kMaxBatch, st)) != cudaSuccess)
+            return e;
         for (uint32_t k = 0; k < batch; ++k) {
-            k_group_scatter<<<ggrid, 128, 0, st>>>(body, body_len, ngroup, w.g_entry, w.g_exit, w.claim);
+            const uint32_t *prev = k ? w.changed + k - 1 : nullptr;
+            k_group_scatter<<<ggrid, 128, 0, st>>>(body, body_len, ngroup, w.g_entry, w.g_exit, w.claim, prev);
             if (round + k == 0) // the first round moves most groups: one warp each
                 k_group_apply<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry,
                                                            w.g_exit, w.g_vis, w.claim, w.changed + k);
             else
                 k_group_apply32<<<wgrid32, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits,
-                                                               w.g_entry, w.g_exit, w.g_vis, w.claim, w.changed + k);
+                                                               w.g_entry, w.g_exit, w.g_vis, w.claim, w.changed + k,
+                                                               prev);
         }
         *launches += 2 * batch;
+        if (fixed_rounds) {
+            unresolved = w.changed + batch - 1;
+            break;
+        }
         uint32_t *changed = thread_pinned_scratch(); // >= kMaxBatch words
         if (!changed)
             return cudaErrorMemoryAllocation;
-        if ((e = peek_u32(changed, w.changed, batch, st)) != cudaSuccess ||
-            (e = cudaMemsetAsync(w.changed, 0, 4 * kMaxBatch, st)) != cudaSuccess ||
-            (e = cudaStreamSynchronize(st)) != cudaSuccess)
+        if ((e = peek_u32(changed, w.changed, batch, st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess)
             return e;
         g_last_rounds = round + batch;
-        if (!changed[batch - 1]) { // a round without change is the fixed point
-            for (uint32_t k = 0; k < batch; ++k)
-                if (!changed[k]) {
-                    g_last_rounds = round + k + 1;
-                    break;
-                }
+        bool converged = false;
+        for (uint32_t k = 0; k < batch; ++k)
+            if (!changed[k]) { // a round without change is the fixed point
+                g_last_rounds = round + k + 1;
+                converged = true;
+                break;
+            }
+        if (converged)
+            break;
+        round += batch;
+        if (round >= max_rounds) {
+            unresolved = w.changed + batch - 1; // (still set: the finish kernel raises ST_UNRESOLVED)
             break;
         }
+        batch = std::min<uint32_t>(batch * 3, kMaxBatch);
     }
     k_group_final<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.outlen,
                                                d_status, open_end);
@@ -906,7 +936,8 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
         k_index_blocks<<<(unsigned)((n_blocks + 255) / 256), 256, 0, st>>>(body, body_len, nseg, w.paths, w.outoff,
                                                                           w.total, body_offset, n_blocks,
                                                                           d_block_offsets, d_status, open_end);
-    k_index_finish<<<1, 32, 0, st>>>(w.total, total_out, stream_bytes, n_blocks, d_block_offsets, d_status, open_end);
+    k_index_finish<<<1, 32, 0, st>>>(w.total, total_out, stream_bytes, n_blocks, d_block_offsets, d_status, open_end,
+                                     unresolved);
     *launches += 6;
     return cudaGetLastError();
 }

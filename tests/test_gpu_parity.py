@@ -388,3 +388,57 @@ print("OK")
     env = dict(os.environ, SNAPPY_B200_DECODER=which)
     r = subprocess.run([sys.executable, "-c", code % (root, root)], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
+
+
+@pytest.mark.gpu
+def test_async_device_api_and_cuda_graph(oracle):
+    """the device-level API only enqueues.  compress + asynchronous index-less decompress are
+    captured into ONE CUDA graph and replayed on new data; the replayed stream must equal the oracle's and
+    the replayed output the input.  Too few relaxation rounds must be reported (ST_UNRESOLVED), not mis-decoded."""
+    import torch
+    n = 24 << 20
+    codec = api.DeviceCodec(n)
+    data = corpus.make_corpus("mixed", n, device="cuda", first_segment=3).clone()
+    out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    hdr = len(oracle.varint_encode(n))
+    # eager run first (also the warm-up a capture needs), and the compressed size of this data
+    codec.compress(data, 0)
+    c_bytes = codec.result_stream().numel()
+    codec.decompress_async(codec.stream_buf, c_bytes, hdr, n, out)
+    codec.check_status()
+    assert torch.equal(out, data)
+    want = oracle.compress(data.cpu().numpy(), 0)
+    _assert_same(codec.result_stream().cpu().numpy(), want, "eager stream")
+    # capture
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    out.zero_()
+    with torch.cuda.stream(side):
+        codec.status.zero_()
+        side.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            codec.compress(data, 0)
+            codec.decompress_async(codec.stream_buf, c_bytes, hdr, n, out, zero_status=False)
+    # replay on the same buffers after scrambling everything the graph writes
+    for _ in range(2):
+        out.zero_()
+        codec.stream_buf.zero_()
+        codec.status.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        codec.check_status()
+        assert int(codec.out_bytes.item()) == c_bytes
+        _assert_same(codec.stream_buf[:c_bytes].cpu().numpy(), want, "replayed stream")
+        assert torch.equal(out, data), "replayed decode"
+    # incompressible data needs far more rounds than 2, and that must be said
+    rnd = corpus.make_corpus("random", n, device="cuda")
+    codec.compress(rnd, 0)
+    cb = codec.result_stream().numel()
+    codec.decompress_async(codec.stream_buf, cb, hdr, n, out, max_rounds=2)
+    torch.cuda.synchronize()
+    assert int(codec.status.item()) & 8, "ST_UNRESOLVED expected"
+    with pytest.raises(api.SnappyError):
+        codec.check_status()
+    codec.decompress_async(codec.stream_buf, cb, hdr, n, out, max_rounds=64)
+    codec.check_status()
+    assert torch.equal(out, rnd)
