@@ -157,6 +157,19 @@ int snappy_b200_compress_host_indexed(const void *in, uint64_t n_bytes, int mode
                                       uint64_t *out_bytes, uint64_t *block_offsets);
 int snappy_b200_decompress_host_indexed(const void *stream, uint64_t stream_bytes, const uint64_t *block_offsets,
                                         uint64_t n_blocks, void *out, uint64_t out_capacity, uint64_t *out_bytes);
+/* The same calls over the first n_devices GPUs of the box: contiguous block ranges per device,
+ * one worker thread and one arena per device, no collective and no peer copy -- the only cross-device datum
+ * is the compressed size of every partition (an exclusive scan on the host places the partitions).  The
+ * stream is byte-identical to the one-device stream.  The index-less decode first runs K0 over the whole
+ * stream on the current device.  The plain calls above forward here when SNAPPY_B200_DEVICES=N (N > 1) is set
+ * and the data is at least 64 MiB.                                                                      */
+int snappy_b200_compress_host_multi(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
+                                    uint64_t *out_bytes, uint64_t *block_offsets, int n_devices);
+int snappy_b200_decompress_host_multi(const void *stream, uint64_t stream_bytes, void *out, uint64_t out_capacity,
+                                      uint64_t *out_bytes, int n_devices);
+int snappy_b200_decompress_host_indexed_multi(const void *stream, uint64_t stream_bytes, const uint64_t *block_offsets,
+                                              uint64_t n_blocks, void *out, uint64_t out_capacity, uint64_t *out_bytes,
+                                              int n_devices);
 /* FILE*-level versions for the command line (`snappy -i`): the index is written to / read from its
  * own file next to the unchanged stream -- "SNPIDX1\0", u64 uncompressed bytes, u64 n_blocks,
  * then n_blocks + 1 u64 stream offsets, all little-endian.  Same FILE* ownership rules as the

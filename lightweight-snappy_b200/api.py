@@ -62,6 +62,11 @@ SIGNATURES = {
                                                     _u8p]),
     "snappy_b200_decompress_host_indexed": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, _u8p, C.c_uint64,
                                                       C.POINTER(C.c_uint64)]),
+    "snappy_b200_compress_host_multi": (C.c_int, [_u8p, C.c_uint64, C.c_int, _u8p, C.c_uint64, C.POINTER(C.c_uint64), _u8p,
+                                                  C.c_int]),
+    "snappy_b200_decompress_host_multi": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]),
+    "snappy_b200_decompress_host_indexed_multi": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, _u8p, C.c_uint64,
+                                                            C.POINTER(C.c_uint64), C.c_int]),
     "snappy_b200_compress_file_indexed": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p]),
     "snappy_b200_decompress_file_indexed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snappy_b200_release": (None, []),
@@ -161,6 +166,33 @@ def decompress_host_indexed(stream, block_offsets, out: np.ndarray | None = None
     n = C.c_uint64(0)
     _check(lib().snappy_b200_decompress_host_indexed(a.ctypes.data, a.size, offs.ctypes.data, offs.size - 1,
                                                      out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value]
+
+
+def compress_host_multi(data, mode: int = MODE_HASH, n_devices: int = 8, with_index: bool = False):
+    """The host-buffer compressor over the first n_devices GPUs (block ranges per device, no collective)."""
+    a = _host_u8(data)
+    out = np.empty(max(max_compressed_bytes(a.size), 1), dtype=np.uint8)
+    offs = np.zeros(block_count(a.size) + 1, dtype=np.uint64)
+    n = C.c_uint64(0)
+    _check(lib().snappy_b200_compress_host_multi(a.ctypes.data, a.size, mode, out.ctypes.data, out.size, C.byref(n),
+                                                 offs.ctypes.data if with_index else None, n_devices))
+    return (out[: n.value], offs) if with_index else out[: n.value]
+
+
+def decompress_host_multi(stream, n_devices: int = 8, block_offsets=None, out: np.ndarray | None = None) -> np.ndarray:
+    a = _host_u8(stream)
+    total = uncompressed_length(a)
+    if out is None:
+        out = np.empty(max(total, 1), dtype=np.uint8)
+    n = C.c_uint64(0)
+    if block_offsets is None:
+        _check(lib().snappy_b200_decompress_host_multi(a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(n),
+                                                       n_devices))
+    else:
+        offs = np.ascontiguousarray(block_offsets, dtype=np.uint64)
+        _check(lib().snappy_b200_decompress_host_indexed_multi(a.ctypes.data, a.size, offs.ctypes.data, offs.size - 1,
+                                                               out.ctypes.data, out.size, C.byref(n), n_devices))
     return out[: n.value]
 
 
@@ -291,6 +323,10 @@ class DeviceCodec:
         st = int(self.status.item())
         if st:
             raise SnappyError(-st, f"device status 0x{st:x}")
+
+
+def device_count() -> int:
+    return int(lib().snappy_b200_device_count())
 
 
 def index_rounds() -> int:

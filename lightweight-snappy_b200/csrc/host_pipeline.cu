@@ -159,7 +159,31 @@ struct HostCtx {
     }
 };
 
-HostCtx g_ctx;
+// One context per device (streams, events and cached buffers belong to a device), each behind its own lock:
+// calls on different devices run concurrently, calls on the same device take turns.
+constexpr int kMaxDevices = 64;
+HostCtx g_ctx_pool[kMaxDevices];
+
+// SNAPPY_B200_DEVICES=N (N > 1): the host-buffer calls shard block ranges over the first N devices
+// (csrc/multi_device.cu) for inputs of at least 64 MiB.  Default 1 = the current device only: under a
+// one-process-per-GPU launcher every rank must stay on its own device.
+int env_devices()
+{
+    const char *v = getenv("SNAPPY_B200_DEVICES");
+    const int n = v ? atoi(v) : 1;
+    return n < 1 ? 1 : n;
+}
+constexpr uint64_t kMultiMin = 64ull << 20;
+
+HostCtx &current_ctx()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        dev = 0;
+    }
+    return g_ctx_pool[(unsigned)dev % kMaxDevices];
+}
 
 // SNAPPY_B200_TRACE=1: timeline of a host call (milliseconds since its first enqueue) on stderr.
 struct Trace {
@@ -350,6 +374,7 @@ int snappy_b200_compress_host_indexed(const void *in, uint64_t n_bytes, int mode
                                       uint64_t *out_bytes, uint64_t *block_offsets)
 {
     clear_error();
+    HostCtx &g_ctx = current_ctx();
     if (!out_bytes || (n_bytes && (!in || !out)))
         return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
     if (mode != SNAPPY_B200_MODE_HASH && mode != SNAPPY_B200_MODE_BST)
@@ -357,6 +382,9 @@ int snappy_b200_compress_host_indexed(const void *in, uint64_t n_bytes, int mode
     *out_bytes = 0;
     if (n_bytes == 0)
         return SNAPPY_B200_OK; // reference: an empty input gives an empty stream
+    if (env_devices() > 1 && n_bytes >= kMultiMin)
+        return snappy_b200_compress_host_multi(in, n_bytes, mode, out, out_capacity, out_bytes, block_offsets,
+                                               env_devices());
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     CU(g_ctx.init(), "context init");
     const uint64_t chunk = std::min<uint64_t>(kCompressChunk, align_up(n_bytes, kBlock));
@@ -474,6 +502,7 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
                                 uint64_t *out_bytes)
 {
     clear_error();
+    HostCtx &g_ctx = current_ctx();
     if (!out_bytes || (stream_bytes && !stream))
         return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
     *out_bytes = 0;
@@ -492,6 +521,8 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
         return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
     if (stream_bytes > max_compressed(total) + 16)
         return fail_msg(SNAPPY_B200_ERR_CORRUPT, "stream is longer than any encoding of its declared length");
+    if (env_devices() > 1 && total >= kMultiMin)
+        return snappy_b200_decompress_host_multi(stream, stream_bytes, out, out_capacity, out_bytes, env_devices());
 
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     CU(g_ctx.init(), "context init");
@@ -587,6 +618,7 @@ int snappy_b200_decompress_host_indexed(const void *stream, uint64_t stream_byte
                                         uint64_t n_blocks, void *out, uint64_t out_capacity, uint64_t *out_bytes)
 {
     clear_error();
+    HostCtx &g_ctx = current_ctx();
     if (!out_bytes || (stream_bytes && !stream) || !block_offsets)
         return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
     *out_bytes = 0;
@@ -610,6 +642,9 @@ int snappy_b200_decompress_host_indexed(const void *stream, uint64_t stream_byte
     for (uint64_t b = 0; b < n_blocks; ++b)
         if (block_offsets[b + 1] <= block_offsets[b] || block_offsets[b + 1] - block_offsets[b] > 2u * kBlock)
             return fail_msg(SNAPPY_B200_ERR_CORRUPT, "the index is not increasing / a block is larger than any 64 KiB block can be");
+    if (env_devices() > 1 && total >= kMultiMin)
+        return snappy_b200_decompress_host_indexed_multi(stream, stream_bytes, block_offsets, n_blocks, out, out_capacity,
+                                                         out_bytes, env_devices());
 
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     CU(g_ctx.init(), "context init");
@@ -691,6 +726,7 @@ int snappy_b200_decompress_device(const uint8_t *d_stream, uint64_t stream_bytes
                                   void *d_workspace, size_t workspace_bytes, void *stream)
 {
     clear_error();
+    HostCtx &g_ctx = current_ctx();
     if (!d_stream || !d_status || !d_workspace || (!d_out && total_out))
         return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
     if (body_offset > stream_bytes || stream_bytes >= (1ull << 40))
@@ -750,8 +786,19 @@ void snappy_b200_host_free(void *p)
 
 void snappy_b200_release(void)
 {
-    std::lock_guard<std::mutex> lock(g_ctx.mu);
-    g_ctx.release();
+    int keep = 0;
+    const bool have = cudaGetDevice(&keep) == cudaSuccess;
+    for (int d = 0; d < kMaxDevices; ++d) {
+        HostCtx &c = g_ctx_pool[d];
+        std::lock_guard<std::mutex> lock(c.mu);
+        if (c.device < 0)
+            continue;
+        if (cudaSetDevice(c.device) == cudaSuccess)
+            c.release();
+    }
+    if (have)
+        cudaSetDevice(keep);
+    (void)cudaGetLastError();
 }
 
 } // extern "C"

@@ -442,3 +442,22 @@ def test_async_device_api_and_cuda_graph(oracle):
     codec.decompress_async(codec.stream_buf, cb, hdr, n, out, max_rounds=64)
     codec.check_status()
     assert torch.equal(out, rnd)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_devices", [1, 2, 8])
+def test_multi_device_host_api(oracle, n_devices):
+    """SURVEY 8e behind the C API: block ranges sharded over the visible devices inside the library.  The
+    stream and the side index must be byte-identical to the oracle's whatever the device count (more devices
+    than the box has are clamped), and both multi-device decoders must invert it."""
+    n = (300 << 20) + 70001 if n_devices > 1 else (70 << 20) + 5
+    data = corpus.make_corpus("mixed", n, device="cuda", first_segment=11).cpu().numpy()
+    want = oracle.compress(data, 0)
+    ref_idx, _ = oracle.block_index(want)
+    stream, offs = api.compress_host_multi(data, api.MODE_HASH, n_devices, with_index=True)
+    _assert_same(stream, want, f"multi-device stream ({n_devices} devices asked, {api.device_count()} present)")
+    assert np.array_equal(offs, ref_idx.astype(np.uint64)), "multi-device side index"
+    _assert_same(api.decompress_host_multi(want, n_devices), data, "multi-device index-less decode")
+    _assert_same(api.decompress_host_multi(want, n_devices, block_offsets=offs), data, "multi-device indexed decode")
+    small = data[: 5 << 20]
+    _assert_same(api.compress_host_multi(small, api.MODE_BST, n_devices), oracle.compress(small, 1), "multi-device BST")
