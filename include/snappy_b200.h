@@ -157,6 +157,16 @@ int snappy_b200_compress_host_indexed(const void *in, uint64_t n_bytes, int mode
                                       uint64_t *out_bytes, uint64_t *block_offsets);
 int snappy_b200_decompress_host_indexed(const void *stream, uint64_t stream_bytes, const uint64_t *block_offsets,
                                         uint64_t n_blocks, void *out, uint64_t out_capacity, uint64_t *out_bytes);
+/* One range of a longer input, for callers that stream (the FILE* layer does): n_bytes must be whole
+ * 64 KiB blocks except for the last range.  varint_value != 0: the range opens the stream, and the preamble
+ * carries that value (the length of the WHOLE input: src/snappy_compression.c:417 writes the declared size);
+ * varint_value == 0: blocks only.  Concatenating the outputs of consecutive ranges gives exactly the stream
+ * of one call over the whole input.  block_offsets (optional) are relative to this range's output.        */
+int snappy_b200_compress_host_range(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
+                                    uint64_t *out_bytes, uint64_t *block_offsets, uint64_t varint_value);
+int snappy_b200_compress_host_multi_range(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
+                                          uint64_t *out_bytes, uint64_t *block_offsets, int n_devices,
+                                          uint64_t varint_value);
 /* The same calls over the first n_devices GPUs of the box: contiguous block ranges per device,
  * one worker thread and one arena per device, no collective and no peer copy -- the only cross-device datum
  * is the compressed size of every partition (an exclusive scan on the host places the partitions).  The

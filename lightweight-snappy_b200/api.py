@@ -64,6 +64,10 @@ SIGNATURES = {
                                                       C.POINTER(C.c_uint64)]),
     "snappy_b200_compress_host_multi": (C.c_int, [_u8p, C.c_uint64, C.c_int, _u8p, C.c_uint64, C.POINTER(C.c_uint64), _u8p,
                                                   C.c_int]),
+    "snappy_b200_compress_host_range": (C.c_int, [_u8p, C.c_uint64, C.c_int, _u8p, C.c_uint64, C.POINTER(C.c_uint64), _u8p,
+                                                  C.c_uint64]),
+    "snappy_b200_compress_host_multi_range": (C.c_int, [_u8p, C.c_uint64, C.c_int, _u8p, C.c_uint64,
+                                                        C.POINTER(C.c_uint64), _u8p, C.c_int, C.c_uint64]),
     "snappy_b200_decompress_host_multi": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]),
     "snappy_b200_decompress_host_indexed_multi": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, _u8p, C.c_uint64,
                                                             C.POINTER(C.c_uint64), C.c_int]),

@@ -76,10 +76,14 @@ static CompressWorkspace carve_compress(void *ws, uint64_t n_bytes)
 
 static int status_to_error(uint32_t st)
 {
+    // FRAMING first: once an element leaves the 64 KiB framing the blocks after it may look malformed to the
+    // block-parallel decoders although the stream is valid; the general decoder is the arbiter then
+    if (st & SNAPPY_B200_ST_FRAMING)
+        return fail(SNAPPY_B200_ERR_FRAMING,
+                    "the stream is not framed in 64 KiB blocks (an element straddles a block or reaches into an "
+                    "earlier one; device status 0x%x)", st);
     if (st & SNAPPY_B200_ST_CORRUPT)
         return fail(SNAPPY_B200_ERR_CORRUPT, "malformed compressed stream (device status 0x%x)", st);
-    if (st & SNAPPY_B200_ST_FRAMING)
-        return fail(SNAPPY_B200_ERR_FRAMING, "an element straddles a 64 KiB block (device status 0x%x)", st);
     if (st & SNAPPY_B200_ST_UNRESOLVED)
         return fail(SNAPPY_B200_ERR_CORRUPT,
                     "the element chain of the stream did not resolve within the relaxation rounds allowed "

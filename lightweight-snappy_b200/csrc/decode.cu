@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(64, MINB) k_decode_seg(const uint8_t *__restri
                                                          const uint64_t *__restrict__ offsets,
                                                          const uint4 *__restrict__ starts, uint64_t total_out,
                                                          uint8_t *out_base, uint32_t *__restrict__ status,
-                                                         uint64_t n_blocks)
+                                                         uint64_t n_blocks, uint64_t blk_base)
 {
     __shared__ SegSmem sm2[2];
     SegSmem &sm = sm2[threadIdx.x >> 5];
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(64, MINB) k_decode_seg(const uint8_t *__restri
                 if (e_hi < ne) {
                     uint32_t ip = sm.elems[e_hi].z, o2 = op + k_hi;
                     const uint32_t tv = ld_le32_any(in + ip, last_word);
-                    err = single_element(in, lim, tv, out, olen, blk, ip, o2, lane);
+                    err = single_element(in, lim, tv, out, olen, blk_base + blk, ip, o2, lane);
                 }
                 e_lo = e_hi + 1;
             }
@@ -519,6 +519,80 @@ __global__ void __launch_bounds__(32) k_decode_warp(const uint8_t *__restrict__ 
         atomicOr(status, err);
 }
 
+// ------------------------------------------------------------------ general decoder (no framing assumed)
+// Raw Snappy allows what no block-framed compressor emits: elements that straddle a 64 KiB output block
+// and copies that reach back into earlier blocks (the reference decoder resolves any offset into its
+// whole-file buffer, src/snappy_decompression.c:349, :253-280, copy-4 :323-327).  The block-parallel
+// decoders report such streams as ST_FRAMING; this kernel then decodes them the way the reference does, one
+// element after the other over the whole output, with one warp moving the bytes of each element.  It is a
+// correctness fallback for rare foreign streams (about an element per microsecond), not a fast path.
+__global__ void __launch_bounds__(32) k_decode_sequential(const uint8_t *__restrict__ stream, uint64_t stream_bytes,
+                                                          uint64_t body_offset, uint64_t total_out, uint8_t *out,
+                                                          uint32_t *__restrict__ status)
+{
+    const uint32_t lane = threadIdx.x;
+    uint64_t ip = body_offset, op = 0;
+    uint32_t err = 0;
+    while (op < total_out) {
+        if (ip >= stream_bytes) {
+            err = SNAPPY_B200_ST_CORRUPT;
+            break;
+        }
+        uint32_t b[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            b[k] = ip + k < stream_bytes ? (uint32_t)__ldg(stream + ip + k) : 0u;
+        const uint32_t tag = b[0], type = tag & 3u;
+        uint64_t hdr, len, off = 0;
+        if (type == 0) {
+            const uint32_t m = tag >> 2;
+            const uint32_t k = m >= 60 ? m - 59 : 0;
+            const uint64_t raw = (uint64_t)b[1] | ((uint64_t)b[2] << 8) | ((uint64_t)b[3] << 16) | ((uint64_t)b[4] << 24);
+            hdr = 1 + k;
+            len = (k == 0 ? m : (raw & (k == 4 ? 0xffffffffull : ((1ull << (8 * k)) - 1)))) + 1;
+            if (ip + hdr + len > stream_bytes || len > total_out - op) {
+                err = SNAPPY_B200_ST_CORRUPT;
+                break;
+            }
+            coop_copy_ro(out + op, stream + ip + hdr, (uint32_t)len, lane, 32);
+            ip += hdr + len;
+        } else {
+            if (type == 1)
+                hdr = 2, len = ((tag >> 2) & 7u) + 4, off = ((uint64_t)(tag >> 5) << 8) | b[1];
+            else if (type == 2)
+                hdr = 3, len = (tag >> 2) + 1, off = (uint64_t)b[1] | ((uint64_t)b[2] << 8);
+            else
+                hdr = 5, len = (tag >> 2) + 1,
+                off = (uint64_t)b[1] | ((uint64_t)b[2] << 8) | ((uint64_t)b[3] << 16) | ((uint64_t)b[4] << 24);
+            if (ip + hdr > stream_bytes || off == 0 || off > op || len > total_out - op) {
+                err = SNAPPY_B200_ST_CORRUPT;
+                break;
+            }
+            __syncwarp(); // the bytes earlier elements wrote are visible to every lane
+            for (uint64_t i = lane; i < len; i += 32) // write_copy :273-280: ascending, so an overlap repeats the pattern
+                out[op + i] = out[op - off + (off >= len ? i : i % off)];
+            ip += hdr;
+        }
+        op += len;
+        __syncwarp();
+    }
+    if (!err && ip != stream_bytes)
+        err = SNAPPY_B200_ST_CORRUPT; // trailing bytes after the declared length
+    if (err && lane == 0)
+        atomicOr(status, err);
+}
+
+cudaError_t launch_decode_sequential(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t body_offset,
+                                     uint64_t total_out, uint8_t *d_out, uint32_t *d_status, cudaStream_t st,
+                                     uint64_t *launches)
+{
+    if (total_out == 0)
+        return cudaSuccess;
+    k_decode_sequential<<<1, 32, 0, st>>>(d_stream, stream_bytes, body_offset, total_out, d_out, d_status);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_decode(const uint8_t *d_stream, const uint64_t *d_offsets, uint64_t n_blocks, uint64_t total_out,
                           uint8_t *d_out, uint32_t *d_status, cudaStream_t st, uint64_t *launches)
 {
@@ -581,7 +655,7 @@ cudaError_t launch_decode_seg(const uint8_t *d_stream, uint64_t body_offset, con
     // two blocks (warps) per CTA and a 48-register cap: 40 warps per SM instead of the 32 that one-warp
     // CTAs allow (measured: 64 registers / 32 warps 6.92, 48 / 40 6.72, 40 / 48 6.84 ms per GiB, K0 included)
     k_decode_seg<20><<<(unsigned)((n_blocks + 1) / 2), 64, 0, st>>>(d_stream, body_offset, d_offsets, d_starts, total_out,
-                                                                    d_out, d_status, n_blocks);
+                                                                    d_out, d_status, n_blocks, blk_base);
     *launches += 1;
     return cudaGetLastError();
 }

@@ -7,6 +7,13 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
 #include "buffer_compression.h"
 #include "snappy_b200.h"
 #include "snappy_compression.h"
@@ -88,50 +95,177 @@ bool read_all(FILE *f, uint64_t hint, PinnedBuf &buf)
 
 const char kIndexMagic[8] = {'S', 'N', 'P', 'I', 'D', 'X', '1', 0};
 
+// The streaming compressor behind snappy_compress / snappy_compress_bst.  The reference works through the file
+// 64 KiB at a time (src/snappy_compression.c:210-213, :419-425); here the unit is a chunk of whole blocks
+// (256 MiB per device in use): a reader thread fills page-locked input buffers, the calling thread runs the
+// GPU pipeline on one chunk while the next is being read, a writer thread appends the finished chunks.
+// Three chunks are in flight, so page-locked memory is bounded by the chunk size, not by the file size.
+struct ChunkQueue { // hands slot numbers from one thread to the next
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<int> q;
+    void push(int v)
+    {
+        {
+            std::lock_guard<std::mutex> l(mu);
+            q.push_back(v);
+        }
+        cv.notify_one();
+    }
+    int pop()
+    {
+        std::unique_lock<std::mutex> l(mu);
+        cv.wait(l, [&] { return !q.empty(); });
+        const int v = q.front();
+        q.pop_front();
+        return v;
+    }
+};
+
+uint64_t stream_chunk_bytes(unsigned long long declared)
+{
+    uint64_t mib = 256;
+    if (const char *v = getenv("SNAPPY_B200_FILE_CHUNK_MIB"))
+        mib = (uint64_t)std::max(1ll, atoll(v));
+    uint64_t dev = 1;
+    if (const char *v = getenv("SNAPPY_B200_DEVICES"))
+        dev = (uint64_t)std::max(1ll, atoll(v));
+    uint64_t chunk = (mib << 20) * dev;
+    const uint64_t whole = ((uint64_t)declared + 65535) / 65536 * 65536;
+    if (declared && whole < chunk)
+        chunk = whole; // a small file: one chunk of its own size (if the file is longer than declared, more follow)
+    return chunk;
+}
+
 int compress_file(FILE *in, unsigned long long declared, FILE *out, int mode, FILE *index_out = nullptr)
 {
-    PinnedBuf data, stream;
     sb200::clear_error();
     if (!in || !out)
         return io_fail("null FILE*");
-    if (!read_all(in, declared, data))
-        return io_fail("reading the input failed (read error or out of host memory)");
-    if (data.empty())
-        return SNAPPY_B200_OK; // reference: empty input -> empty output
-    if (!stream.reserve(snappy_b200_max_compressed_bytes(data.size())))
-        return io_fail("out of host memory for the compressed stream");
-    uint64_t n = 0;
-    const uint64_t nb = snappy_b200_block_count(data.size());
-    uint64_t *offsets = index_out ? static_cast<uint64_t *>(malloc((nb + 1) * 8)) : nullptr;
-    if (index_out && !offsets)
-        return io_fail("out of host memory for the block index");
-    struct Free {
-        void *p;
-        ~Free() { free(p); }
-    } free_offsets{offsets};
-    const int rc =
-        snappy_b200_compress_host_indexed(data.data(), data.size(), mode, stream.data(), stream.cap, &n, offsets);
+    constexpr int kInFlight = 3;
+    const uint64_t chunk = stream_chunk_bytes(declared);
+    const uint64_t out_cap = snappy_b200_max_compressed_bytes(chunk);
+    PinnedBuf ibuf[kInFlight], obuf[kInFlight];
+    uint64_t ilen[kInFlight] = {}, olen[kInFlight] = {};
+    ChunkQueue free_in, filled, to_write, free_out;
+    bool read_error = false, write_error = false;
+    int rc = SNAPPY_B200_OK;
+
+    // reader: fills input slots until EOF (a slot with 0 bytes marks the end)
+    std::thread reader([&] {
+        for (;;) {
+            const int s = free_in.pop();
+            if (s < 0)
+                return; // the caller gave up
+            const int c = fgetc(in); // (no page-locked buffer is set up just to find the end of the file)
+            if (c == EOF) {
+                if (ferror(in))
+                    read_error = true;
+                ilen[s] = 0;
+                filled.push(s);
+                return;
+            }
+            ungetc(c, in);
+            if (!ibuf[s].reserve(chunk)) {
+                read_error = true;
+                ilen[s] = 0;
+                filled.push(s);
+                return;
+            }
+            uint64_t got = 0;
+            while (got < chunk) {
+                const size_t k = fread(ibuf[s].p + got, 1, chunk - got, in);
+                if (k == 0)
+                    break;
+                got += k;
+            }
+            if (ferror(in))
+                read_error = true;
+            ilen[s] = read_error ? 0 : got;
+            filled.push(s);
+            if (got < chunk)
+                return;
+        }
+    });
+    // writer: appends finished chunks in order (a negative slot ends it)
+    std::thread writer([&] {
+        for (;;) {
+            const int s = to_write.pop();
+            if (s < 0)
+                return;
+            if (!write_error && fwrite(obuf[s].p, 1, olen[s], out) != olen[s])
+                write_error = true;
+            free_out.push(s);
+        }
+    });
+    for (int s = 0; s < kInFlight; ++s) {
+        free_in.push(s);
+        free_out.push(s);
+    }
+    std::vector<uint64_t> index; // stream offset of every block, when an index file is wanted
+    std::vector<uint64_t> offs;
+    uint64_t n_in = 0, n_out = 0;
+    bool first = true, ended = false;
+    while (!ended) {
+        const int s = filled.pop();
+        const uint64_t n = ilen[s];
+        if (n < chunk)
+            ended = true; // the last chunk (possibly empty)
+        if (n == 0) {
+            free_in.push(s);
+            break;
+        }
+        const int o = free_out.pop();
+        if (rc == SNAPPY_B200_OK && !obuf[o].reserve(out_cap))
+            rc = io_fail("out of host memory for the compressed stream");
+        uint64_t got = 0;
+        const uint64_t nb = snappy_b200_block_count(n);
+        if (index_out)
+            offs.resize(nb + 1);
+        if (rc == SNAPPY_B200_OK)
+            // the reference writes the DECLARED size into the preamble (src/snappy_compression.c:417) and then
+            // whatever the file really holds: keep that even when the two disagree
+            rc = snappy_b200_compress_host_range(ibuf[s].p, n, mode, obuf[o].p, obuf[o].cap, &got,
+                                                 index_out ? offs.data() : nullptr,
+                                                 first ? (declared ? declared : ~0ull) : 0);
+        if (rc == SNAPPY_B200_OK && first && declared == 0) {
+            // (a declared size of 0 still needs its one-byte preamble "00": ask for any value, then patch it)
+            unsigned char tmp[10];
+            const unsigned k = parse_to_varint(~0ull, tmp);
+            memmove(obuf[o].p + 1, obuf[o].p + k, got - k);
+            obuf[o].p[0] = 0;
+            for (uint64_t b = 0; index_out && b <= nb; ++b)
+                offs[b] -= k - 1;
+            got -= k - 1;
+        }
+        if (rc == SNAPPY_B200_OK && index_out)
+            for (uint64_t b = 0; b < nb; ++b)
+                index.push_back(n_out + offs[b]);
+        first = false;
+        olen[o] = rc == SNAPPY_B200_OK ? got : 0;
+        n_in += n;
+        n_out += olen[o];
+        to_write.push(o);
+        free_in.push(s); // (the reader blocks in pop() at most once more; it returns on the -1 below)
+    }
+    free_in.push(-1);
+    to_write.push(-1);
+    reader.join();
+    writer.join();
     if (rc != SNAPPY_B200_OK)
-        return rc; // (the message is in snappy_b200_last_error())
-    // The reference writes the DECLARED size into the preamble (src/snappy_compression.c:417)
-    // and then whatever the file really held; keep that even when the two disagree.
-    unsigned char hdr[10];
-    const unsigned hdr_real = parse_to_varint(data.size(), hdr);
-    const unsigned hdr_decl = parse_to_varint(declared, hdr);
-    if (fwrite(hdr, 1, hdr_decl, out) != hdr_decl)
+        return rc;
+    if (read_error)
+        return io_fail("reading the input failed (read error or out of host memory)");
+    if (write_error)
         return io_fail("short write of the compressed stream");
-    if (fwrite(stream.data() + hdr_real, 1, n - hdr_real, out) != n - hdr_real)
-        return io_fail("short write of the compressed stream");
-    if (index_out) {
-        // offsets as they are in the file just written (the declared-size preamble may be longer or shorter)
-        for (uint64_t b = 0; b <= nb; ++b)
-            offsets[b] = offsets[b] - hdr_real + hdr_decl;
-        const uint64_t head[2] = {data.size(), nb};
+    if (index_out && n_in) {
+        index.push_back(n_out);
+        const uint64_t head[2] = {n_in, (uint64_t)index.size() - 1};
         if (fwrite(kIndexMagic, 1, 8, index_out) != 8 || fwrite(head, 8, 2, index_out) != 2 ||
-            fwrite(offsets, 8, nb + 1, index_out) != nb + 1)
+            fwrite(index.data(), 8, index.size(), index_out) != index.size())
             return io_fail("short write of the block index");
     }
-    return SNAPPY_B200_OK;
+    return SNAPPY_B200_OK; // (an empty input leaves an empty output, like the reference: SURVEY.md 8c)
 }
 
 } // namespace

@@ -48,6 +48,8 @@ const uint64_t *index_total(void *, uint64_t);
 const uint64_t *compress_chunk_offsets(void *, uint64_t);
 cudaError_t launch_decode(const uint8_t *, const uint64_t *, uint64_t, uint64_t, uint8_t *, uint32_t *, cudaStream_t,
                           uint64_t *);
+cudaError_t launch_decode_sequential(const uint8_t *, uint64_t, uint64_t, uint64_t, uint8_t *, uint32_t *, cudaStream_t,
+                                     uint64_t *);
 const uint64_t *index_outoff(void *, uint64_t);
 cudaError_t launch_decode_seg(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, const uint64_t *, uint64_t, uint64_t, uint8_t *,
                               uint32_t *, uint64_t, cudaStream_t, uint64_t *);
@@ -373,6 +375,12 @@ int snappy_b200_compress_host(const void *in, uint64_t n_bytes, int mode, void *
 int snappy_b200_compress_host_indexed(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
                                       uint64_t *out_bytes, uint64_t *block_offsets)
 {
+    return snappy_b200_compress_host_range(in, n_bytes, mode, out, out_capacity, out_bytes, block_offsets, n_bytes);
+}
+
+int snappy_b200_compress_host_range(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
+                                    uint64_t *out_bytes, uint64_t *block_offsets, uint64_t varint_value)
+{
     clear_error();
     HostCtx &g_ctx = current_ctx();
     if (!out_bytes || (n_bytes && (!in || !out)))
@@ -383,8 +391,8 @@ int snappy_b200_compress_host_indexed(const void *in, uint64_t n_bytes, int mode
     if (n_bytes == 0)
         return SNAPPY_B200_OK; // reference: an empty input gives an empty stream
     if (env_devices() > 1 && n_bytes >= kMultiMin)
-        return snappy_b200_compress_host_multi(in, n_bytes, mode, out, out_capacity, out_bytes, block_offsets,
-                                               env_devices());
+        return snappy_b200_compress_host_multi_range(in, n_bytes, mode, out, out_capacity, out_bytes, block_offsets,
+                                                     env_devices(), varint_value);
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     CU(g_ctx.init(), "context init");
     const uint64_t chunk = std::min<uint64_t>(kCompressChunk, align_up(n_bytes, kBlock));
@@ -428,7 +436,7 @@ int snappy_b200_compress_host_indexed(const void *in, uint64_t n_bytes, int mode
         if (e == cudaSuccess)
             e = cudaMemsetAsync(d_bytes, 0, 16, st);
         if (e == cudaSuccess)
-            e = compress_chunk(static_cast<const uint8_t *>(g_ctx.buf[0 + s]), len, j == 0 ? n_bytes : 0, mode,
+            e = compress_chunk(static_cast<const uint8_t *>(g_ctx.buf[0 + s]), len, j == 0 ? varint_value : 0, mode,
                                static_cast<uint8_t *>(g_ctx.buf[4 + s]), out_cap_chunk, d_bytes, d_status,
                                g_ctx.buf[8 + s], st);
         if (e == cudaSuccess)
@@ -498,8 +506,8 @@ int snappy_b200_uncompressed_length(const void *stream, uint64_t stream_bytes, u
     return SNAPPY_B200_OK;
 }
 
-int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void *out, uint64_t out_capacity,
-                                uint64_t *out_bytes)
+static int decompress_host_framed(const void *stream, uint64_t stream_bytes, void *out, uint64_t out_capacity,
+                                  uint64_t *out_bytes)
 {
     clear_error();
     HostCtx &g_ctx = current_ctx();
@@ -609,6 +617,46 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
         return status_error(status);
     *out_bytes = total;
     return SNAPPY_B200_OK;
+}
+
+// Valid raw Snappy that is not framed in 64 KiB blocks (straddling elements, copies into earlier blocks):
+// decoded like the reference does, one element after the other (k_decode_sequential).
+static int decompress_host_general(const void *stream, uint64_t stream_bytes, void *out, uint64_t *out_bytes)
+{
+    HostCtx &g_ctx = current_ctx();
+    uint64_t total = 0;
+    const unsigned hdr = host_varint_decode(static_cast<const uint8_t *>(stream), stream_bytes, &total);
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    CU(g_ctx.init(), "context init");
+    CU(g_ctx.need(0, stream_bytes + 64), "cudaMalloc");
+    CU(g_ctx.need(1, total), "cudaMalloc");
+    CU(g_ctx.need(6, 256), "cudaMalloc");
+    uint32_t *d_status = static_cast<uint32_t *>(g_ctx.buf[6]);
+    uint64_t launches = 0;
+    CU(cudaMemcpyAsync(g_ctx.buf[0], stream, stream_bytes, cudaMemcpyHostToDevice, g_ctx.s_run), "H2D copy");
+    CU(cudaMemsetAsync(d_status, 0, 4, g_ctx.s_run), "memset");
+    CU(launch_decode_sequential(static_cast<const uint8_t *>(g_ctx.buf[0]), stream_bytes, hdr, total,
+                                static_cast<uint8_t *>(g_ctx.buf[1]), d_status, g_ctx.s_run, &launches),
+       "decode launch");
+    add_launches(launches);
+    CU(cudaMemcpyAsync(out, g_ctx.buf[1], total, cudaMemcpyDeviceToHost, g_ctx.s_run), "D2H copy");
+    CU(peek_u32(reinterpret_cast<uint32_t *>(g_ctx.h_small + 1), d_status, 1, g_ctx.s_run), "read-back");
+    CU(cudaStreamSynchronize(g_ctx.s_run), "decode");
+    const uint32_t status = (uint32_t)g_ctx.h_small[1];
+    if (status)
+        return status_error(status);
+    *out_bytes = total;
+    return SNAPPY_B200_OK;
+}
+
+int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void *out, uint64_t out_capacity,
+                                uint64_t *out_bytes)
+{
+    const int rc = decompress_host_framed(stream, stream_bytes, out, out_capacity, out_bytes);
+    if (rc != SNAPPY_B200_ERR_FRAMING)
+        return rc;
+    clear_error();
+    return decompress_host_general(stream, stream_bytes, out, out_bytes); // (all arguments were checked above)
 }
 
 // ---- decode with the side index: no K0.  The stream goes up in pieces cut at block boundaries

@@ -132,6 +132,14 @@ extern "C" {
 int snappy_b200_compress_host_multi(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
                                     uint64_t *out_bytes, uint64_t *block_offsets, int n_devices)
 {
+    return snappy_b200_compress_host_multi_range(in, n_bytes, mode, out, out_capacity, out_bytes, block_offsets, n_devices,
+                                                 n_bytes);
+}
+
+int snappy_b200_compress_host_multi_range(const void *in, uint64_t n_bytes, int mode, void *out, uint64_t out_capacity,
+                                          uint64_t *out_bytes, uint64_t *block_offsets, int n_devices,
+                                          uint64_t varint_value)
+{
     clear_error();
     if (!out_bytes || (n_bytes && (!in || !out)))
         return fail_msg(SNAPPY_B200_ERR_ARG, "null pointer argument");
@@ -183,7 +191,7 @@ int snappy_b200_compress_host_multi(const void *in, uint64_t n_bytes, int mode, 
             uint8_t *slot = d_in + (c & 1) * chunk;
             W(cudaMemcpyAsync(slot, src + clo, len, cudaMemcpyHostToDevice, a.st), "H2D copy");
             W(cudaMemsetAsync(d_small, 0, 16, a.st), "memset");
-            W(compress_chunk(slot, len, (g == 0 && c == 0) ? n_bytes : 0, mode, d_out + doff, max_compressed(len), d_small,
+            W(compress_chunk(slot, len, (g == 0 && c == 0) ? varint_value : 0, mode, d_out + doff, max_compressed(len), d_small,
                              reinterpret_cast<uint32_t *>(d_small + 1), a.buf[2], a.st),
               "compress launch");
             W(cudaMemcpyAsync(a.h_small, d_small, 16, cudaMemcpyDeviceToHost, a.st), "read-back");

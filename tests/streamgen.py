@@ -45,6 +45,37 @@ def _copy(rng, length: int, off: int) -> bytes:
     return forms[int(rng.integers(0, len(forms)))]
 
 
+def make_crossing_stream(seed: int, total: int) -> tuple[np.ndarray, np.ndarray]:
+    """Valid raw Snappy that is NOT framed in 64 KiB blocks: elements straddle the 64 KiB output
+    boundaries, copies reach back further than 64 KiB (copy-4 with 32-bit offsets) and into earlier
+    blocks.  The reference decoder resolves all of it in its whole-file buffer
+    (src/snappy_decompression.c:253-280, :323-327).  Returns (stream, expected output)."""
+    rng = np.random.default_rng(seed)
+    out = bytearray()
+    stream = bytearray(_varint(total))
+    while len(out) < total:
+        room = total - len(out)
+        if len(out) == 0 or rng.random() < 0.3:
+            n = int(min(room, rng.choice([1, 7, 60, 61, 300, 5000, 70000])))
+            data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+            stream += _literal(rng, data)
+            out += data
+        else:
+            n = int(min(room, rng.integers(1, 65)))
+            r = rng.random()
+            if r < 0.3:
+                off = int(rng.integers(1, min(len(out), 70) + 1))
+            elif r < 0.6:
+                off = int(rng.integers(1, min(len(out), 65535) + 1))
+            else:
+                off = int(rng.integers(1, len(out) + 1))  # anywhere in the output so far: often > 64 KiB back
+            stream += _copy(rng, n, off)
+            start = len(out) - off
+            for i in range(n):
+                out.append(out[start + i])
+    return np.frombuffer(bytes(stream), np.uint8).copy(), np.frombuffer(bytes(out), np.uint8).copy()
+
+
 def make_stream(seed: int, total: int, style: str = "mixed") -> tuple[np.ndarray, np.ndarray]:
     """Returns (stream, expected output)."""
     rng = np.random.default_rng(seed)

@@ -461,3 +461,69 @@ def test_multi_device_host_api(oracle, n_devices):
     _assert_same(api.decompress_host_multi(want, n_devices, block_offsets=offs), data, "multi-device indexed decode")
     small = data[: 5 << 20]
     _assert_same(api.compress_host_multi(small, api.MODE_BST, n_devices), oracle.compress(small, 1), "multi-device BST")
+
+
+@pytest.mark.gpu
+def test_unframed_foreign_streams(oracle):
+    """valid raw Snappy whose elements straddle 64 KiB output blocks and whose copies reach
+    into earlier blocks (tests/streamgen.py::make_crossing_stream).  The host API must decode it exactly
+    like the oracle decoder (the block-parallel path reports FRAMING, the general decoder takes over);
+    truly malformed variants of the same streams must still be rejected."""
+    import streamgen
+    for seed, total in enumerate([70000, 200000, 1 << 20, (3 << 20) + 17]):
+        stream, want = streamgen.make_crossing_stream(3000 + seed, total)
+        assert np.array_equal(oracle.decompress(stream), want)
+        _assert_same(api.snappy_decompress(stream), want, f"crossing stream {seed} ({total} bytes)")
+        # cut short / offset beyond the output so far / trailing garbage: errors, not wrong output
+        for bad in (stream[:-1], np.concatenate([stream, np.zeros(3, np.uint8)])):
+            with pytest.raises(api.SnappyError):
+                api.snappy_decompress(bad)
+    # a copy that reaches before the start of the output
+    bad = np.frombuffer(b"\x90\x4e" + b"\x0cabcd" + bytes([(63 << 2) | 3, 5, 0, 0, 0]) + b"\x00" * 8, np.uint8)
+    with pytest.raises(api.SnappyError):
+        api.snappy_decompress(bad)
+
+
+@pytest.mark.gpu
+def test_streaming_file_layer(tmp_path, oracle, monkeypatch):
+    """The FILE* drop-in layer streams: chunks of whole blocks through three page-locked buffers (reader
+    thread / GPU pipeline / writer thread), so memory is bounded by the chunk size.  With a 4 MiB chunk a
+    70 MB file goes through ~17 chunks; the stream, the side index and the round trip must not notice.
+    Also: a declared size that disagrees with the file (the reference writes the declared one,
+    src/snappy_compression.c:417) and an input that ends exactly on a chunk boundary."""
+    import subprocess
+    monkeypatch.setenv("SNAPPY_B200_FILE_CHUNK_MIB", "4")
+    for n in ((70 << 20) + 4321, 8 << 20):
+        data = corpus.make_corpus("mixed", n, device="cuda", first_segment=5).cpu().numpy()
+        src, comp, back, bst = (tmp_path / x for x in ("in.bin", "c.snp", "back.bin", "c.bsnp"))
+        src.write_bytes(data.tobytes())
+        env = dict(os.environ)
+        subprocess.run([api.CLI_PATH, "-c", "-i", str(src), str(comp)], check=True, timeout=300, env=env)
+        got = np.fromfile(comp, np.uint8)
+        want = oracle.compress(data, 0)
+        _assert_same(got, want, f"streamed -c stream ({n} bytes)")
+        idx = np.fromfile(str(comp) + ".idx", np.uint64)
+        ref_idx, _ = oracle.block_index(want)
+        assert idx[1] == n and idx[2] == api.block_count(n) and np.array_equal(idx[3:], ref_idx.astype(np.uint64))
+        subprocess.run([api.CLI_PATH, "-d", str(comp), str(back)], check=True, timeout=300, env=env)
+        assert np.array_equal(np.fromfile(back, np.uint8), data)
+    small = data[: 3 << 20]
+    src.write_bytes(small.tobytes())
+    subprocess.run([api.CLI_PATH, "-b", str(src), str(bst)], check=True, timeout=300, env=env)
+    _assert_same(np.fromfile(bst, np.uint8), oracle.compress(small, 1), "streamed -b stream")
+    # the library call with a wrong declared size: preamble = declared, body = what the file holds
+    import ctypes as C
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    L = api.lib()
+    L.snappy_compress.restype = None
+    L.snappy_compress.argtypes = [C.c_void_p, C.c_ulonglong, C.c_void_p]
+    fi, fo = libc.fopen(str(src).encode(), b"rb"), libc.fopen(str(comp).encode(), b"wb")
+    L.snappy_compress(fi, 12345, fo)
+    libc.fclose(fi), libc.fclose(fo)
+    got = np.fromfile(comp, np.uint8)
+    want = oracle.compress(small, 0)
+    hdr = len(oracle.varint_encode(small.size))
+    assert got[:2].tobytes() == oracle.varint_encode(12345) and np.array_equal(got[2:], want[hdr:])
