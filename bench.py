@@ -373,6 +373,24 @@ def run_gpu_arm(args) -> None:
         barrier()
         return max_over_ranks(dt)
 
+    # the box's host<->device ceiling with all ranks copying at once (the end-to-end numbers are bounded by it:
+    # profiles/r02_pcie_ceiling_8gpu.json) -- the same page-locked buffers, plain copies, best of 3
+    def link_rate(fn, nbytes):
+        best = None
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize(dev)
+            dt = max_over_ranks(time.perf_counter() - t0)
+            best = dt if best is None else min(best, dt)
+        return sum_over_ranks(float(nbytes)) / best / 1e9
+
+    h2d_rate = link_rate(lambda: data.copy_(h_data, non_blocking=True), n)
+    d2h_rate = link_rate(lambda: h_out.copy_(out, non_blocking=True), n)
+    data.copy_(h_data)
+    torch.cuda.synchronize(dev)
+
     got = {}
 
     def e2e_decomp():
@@ -441,14 +459,21 @@ def run_gpu_arm(args) -> None:
             "decompress_unpipelined_ms_per_step": td["unpipelined_ms_per_step"],
             "e2e": {"value": total_u * e2e_steps / dt_d / 1e9, "unit": "GB/s", "h2d_bytes_per_step": c_bytes,
                     "d2h_bytes_per_step": n, "steps": e2e_steps,
-                    "api": "snappy_b200_decompress_host (pinned host buffers)"},
+                    "api": "snappy_b200_decompress_host (pinned host buffers)",
+                    "link_ceiling": {"h2d_GBs": h2d_rate, "d2h_GBs": d2h_rate,
+                                     "how": "all ranks copying 1 GiB page-locked buffers at once, best of 3"},
+                    # full duplex: the step cannot beat the slower of its upload and its download
+                    "frac_of_link_ceiling": (total_u * e2e_steps / dt_d / 1e9) /
+                                            (total_u / max(total_c / h2d_rate, total_u / d2h_rate))},
             "gpu_launches": td["launches"],
             "clocks": td["clocks"],
             "compress": {
                 "value": total_u * args.steps / (tc["total_ms"] * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_c,
                 "roofline": roofline(tc, float(n + c_bytes)),
                 "e2e": {"value": total_u * e2e_steps / dt_c / 1e9, "unit": "GB/s", "h2d_bytes_per_step": n,
-                        "d2h_bytes_per_step": c_bytes, "api": "snappy_b200_compress_host (pinned host buffers)"},
+                        "d2h_bytes_per_step": c_bytes, "api": "snappy_b200_compress_host (pinned host buffers)",
+                        "frac_of_link_ceiling": (total_u * e2e_steps / dt_c / 1e9) /
+                                                (total_u / max(total_u / h2d_rate, total_c / d2h_rate))},
                 "gpu_launches": tc["launches"], "clocks": tc["clocks"],
                 "parity": "stream byte-identical to the oracle is asserted in tests/ and smoke(); here the "
                           "round trip and the K0 index are asserted before timing",
