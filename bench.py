@@ -43,7 +43,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 GIB = 1 << 30
 SEED = 20261018
 METRIC = "decompress GB/s (uncompressed)"
-DECODE_KERNEL = "k_decode_win (+ k_copy_literal_blocks)"
+DECODE_KERNEL = "k_decode_seg (+ k_copy_literal_blocks)"
 
 
 # ------------------------------------------------------------------------------ CPU baseline
@@ -251,7 +251,7 @@ def run_gpu_arm(args) -> None:
 
     def step_decode_kernel(ev=None):
         # the two halves called separately over the whole stream, so that the dominant kernel pair
-        # (k_copy_literal_blocks + k_decode_win, one launch each over all 16384 blocks) is bracketed by its own pair of events
+        # (k_copy_literal_blocks + k_decode_seg, one launch each over all 16384 blocks) is bracketed by its own pair of events
         codec.index(stream, c_bytes, hdr, n, k0_index)
         if ev:
             ev[0].record()

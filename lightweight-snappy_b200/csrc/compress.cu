@@ -41,6 +41,7 @@
 #include <cstdlib>
 
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -84,28 +85,39 @@ __device__ __forceinline__ uint32_t match_extend(const uint8_t *__restrict__ b, 
 // GLOBAL: the table lives in global memory (the big tier, see launch_compress).  It is private to
 // one warp, but lanes insert with atomics, which are performed in L2: the reads then go to L2 as
 // well (__ldcg) instead of trusting a line in L1.
+// In the global tiers an entry is 32 bits: the position and a 16-bit fingerprint of the key (the low half
+// of key * golden; the high bits give the home slot).  A probe that walks over other keys' entries then
+// costs one L2 access per entry instead of two dependent ones (entry, then the key bytes through the
+// block): the key bytes are only fetched when the fingerprint matches, i.e. practically only on a hit.
 template <int LOG_SLOTS, bool GLOBAL = false> struct ExactTable {
     static constexpr uint32_t kSlots = 1u << LOG_SLOTS;
-    static constexpr uint32_t kEmpty = 0xffffu;
-    uint16_t *tab;
+    using Entry = typename std::conditional<GLOBAL, uint32_t, uint16_t>::type;
+    static constexpr uint32_t kEmpty = GLOBAL ? 0xffffffffu : 0xffffu;
+    static constexpr uint32_t kBytes = kSlots * sizeof(Entry);
+    Entry *tab;
 
     __device__ __forceinline__ uint32_t home(uint32_t key) const { return (key * 0x9e3779b1u) >> (32 - LOG_SLOTS); }
+    __device__ __forceinline__ uint32_t entry(uint32_t key, uint32_t pos) const
+    {
+        return GLOBAL ? pos | ((key * 0x9e3779b1u) << 16) : pos;
+    }
 
     // Returns the slot holding `key`, or the first empty slot of its probe sequence.
     __device__ __forceinline__ uint32_t find(const uint8_t *__restrict__ b, uint32_t last_word, uint32_t key,
                                              bool &found, uint32_t &pos) const
     {
         uint32_t s = home(key);
+        const uint32_t fp = (key * 0x9e3779b1u) & 0xffffu;
         for (;;) {
-            const uint32_t v = GLOBAL ? __ldcg(tab + s) : tab[s];
+            const uint32_t v = GLOBAL ? (uint32_t)__ldcg(tab + s) : (uint32_t)tab[s];
             if (v == kEmpty) {
                 found = false;
                 pos = 0;
                 return s;
             }
-            if (ld_be32(b, v, last_word) == key) {
+            if ((!GLOBAL || (v >> 16) == fp) && ld_be32(b, v & 0xffffu, last_word) == key) {
                 found = true;
-                pos = v;
+                pos = v & 0xffffu;
                 return s;
             }
             s = (s + 1) & (kSlots - 1);
@@ -117,13 +129,19 @@ template <int LOG_SLOTS, bool GLOBAL = false> struct ExactTable {
     {
         uint32_t s = home(key);
         for (;;) {
-            const unsigned short old = atomicCAS(reinterpret_cast<unsigned short *>(tab + s),
-                                                 (unsigned short)kEmpty, (unsigned short)pos);
-            if (old == kEmpty)
-                return;
+            if (GLOBAL) {
+                if (atomicCAS(reinterpret_cast<unsigned int *>(tab + s), kEmpty, entry(key, pos)) == kEmpty)
+                    return;
+            } else {
+                const unsigned short old = atomicCAS(reinterpret_cast<unsigned short *>(tab + s),
+                                                     (unsigned short)kEmpty, (unsigned short)pos);
+                if (old == kEmpty)
+                    return;
+            }
             s = (s + 1) & (kSlots - 1);
         }
     }
+    __device__ __forceinline__ void set(uint32_t slot, uint32_t key, uint32_t pos) { tab[slot] = (Entry)entry(key, pos); }
 };
 
 // ------------------------------------------------------------------------------- the parse
@@ -152,7 +170,7 @@ __device__ __forceinline__ void parse_block(const uint8_t *__restrict__ in, uint
 
     uint16_t *hpos = reinterpret_cast<uint16_t *>(smem_raw);   // hash mode: candidate position per slot
     uint8_t *hfp = fp_mem ? fp_mem : smem_raw + 2 * SNAPPY_B200_HTABLE_SIZE; // hash mode: key fingerprint per slot
-    ExactTable<LOG_SLOTS, GLOBAL> et{reinterpret_cast<uint16_t *>(smem_raw)};
+    ExactTable<LOG_SLOTS, GLOBAL> et{reinterpret_cast<typename ExactTable<LOG_SLOTS, GLOBAL>::Entry *>(smem_raw)};
     uint32_t shift = 20;
     uint32_t n_keys = 0; // exact mode: dictionary population (warp-uniform)
 
@@ -173,7 +191,7 @@ __device__ __forceinline__ void parse_block(const uint8_t *__restrict__ in, uint
     } else {
         uint4 *t4 = reinterpret_cast<uint4 *>(smem_raw);
         const uint4 init = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        for (uint32_t i = lane; i < ExactTable<LOG_SLOTS, GLOBAL>::kSlots / 8; i += 32)
+        for (uint32_t i = lane; i < ExactTable<LOG_SLOTS, GLOBAL>::kBytes / 16; i += 32)
             t4[i] = init;
     }
     __syncwarp();
@@ -364,7 +382,7 @@ __device__ __forceinline__ void parse_block(const uint8_t *__restrict__ in, uint
             uint32_t tpos;
             const uint32_t slot = et.find(b, last_word, key, found, tpos); // found_match_tree tree.c:174-180
             if (found) {
-                et.tab[slot] = (uint16_t)pos; // tree.c:221 (every lane stores the same value)
+                et.set(slot, key, pos); // tree.c:221 (every lane stores the same value)
                 const uint32_t len = match_extend(b, pos, tpos, n, last_word, lane);
                 if (lane == (nh & 31u))
                     rec = make_uint2(pos | ((pos - tpos) << 16), len | ((pos - prev_end) << 16));
@@ -479,7 +497,7 @@ __device__ __forceinline__ void parse_block(const uint8_t *__restrict__ in, uint
                     bool fnd;
                     uint32_t tp;
                     const uint32_t s = et.find(b, last_word, key, fnd, tp);
-                    et.tab[s] = (uint16_t)ev_pos;
+                    et.set(s, key, ev_pos);
                 }
             }
             const uint32_t e4 = __shfl_sync(kFull, ext4, f);
@@ -531,7 +549,7 @@ __global__ void __launch_bounds__(32) k_parse_exact_global(const uint8_t *__rest
                                                            uint32_t *__restrict__ nrec, uint8_t *__restrict__ tables,
                                                            uint32_t *__restrict__ counter, int only_marked)
 {
-    uint8_t *table = tables + (size_t)blockIdx.x * ((size_t)2 << LOG_SLOTS);
+    uint8_t *table = tables + (size_t)blockIdx.x * ((size_t)4 << LOG_SLOTS); // 32-bit entries (position + fingerprint)
     for (;;) {
         uint32_t blk = 0;
         if (threadIdx.x == 0)
@@ -785,7 +803,7 @@ cudaError_t launch_compress(const uint8_t *d_in, uint64_t n_bytes, int mode, uin
         else
             k_parse_exact_global<13, false><<<(unsigned)chains, cta, 0, st>>>(d_in, n_bytes, nb, d_recs, d_nrec,
                                                                               d_scratch, counters + 1, 0);
-        const uint64_t n_big = std::min<uint64_t>(area / ((uint64_t)2 << kGlobalTierLog), chains);
+        const uint64_t n_big = std::min<uint64_t>(area / ((uint64_t)4 << kGlobalTierLog), chains);
         if (n_big >= 1 && !smem_tables) {
             k_parse_exact_global<kGlobalTierLog, true><<<(unsigned)n_big, cta, 0, st>>>(d_in, n_bytes, nb, d_recs, d_nrec,
                                                                                      d_scratch, counters + 2, 1);
