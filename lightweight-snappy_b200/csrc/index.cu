@@ -184,8 +184,10 @@ __device__ __forceinline__ void group_stage(GroupStage &sm, uint64_t g, uint64_t
 
 // Writes the (possibly improved) per-segment records back, so that later passes find the chain
 // on the recorded paths.
+// `entries` keeps the entry offset of every segment on the chain just resolved (kDead: none), so that the
+// last pass does not have to resolve the group once more.
 __device__ __forceinline__ void group_unstage(const GroupStage &sm, uint64_t g, uint64_t nseg, uint4 *__restrict__ paths,
-                                              uint64_t *__restrict__ exits)
+                                              uint64_t *__restrict__ exits, uint8_t *__restrict__ entries)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t s0 = g * kGroup;
@@ -194,6 +196,7 @@ __device__ __forceinline__ void group_unstage(const GroupStage &sm, uint64_t g, 
         if (s0 + k < nseg) {
             paths[s0 + k] = sm.paths[k];
             exits[s0 + k] = sm.exits[k];
+            entries[s0 + k] = sm.entry[k];
         }
 }
 
@@ -312,7 +315,8 @@ __global__ void __launch_bounds__(kGroupCta) k_group_init(const uint8_t *__restr
                                                           uint64_t *__restrict__ exits,
                                                           uint32_t *__restrict__ g_entry, uint64_t *__restrict__ g_exit,
                                                           uint64_t *__restrict__ g_vis,
-                                                          unsigned long long *__restrict__ g_claim)
+                                                          unsigned long long *__restrict__ g_claim,
+                                                          uint8_t *__restrict__ entries)
 {
     __shared__ GroupStage stage[kGroupCta / 32];
     const uint64_t g = blockIdx.x * (uint64_t)(kGroupCta / 32) + (threadIdx.x >> 5);
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(kGroupCta) k_group_init(const uint8_t *__restr
     group_stage(sm, g, nseg, paths, exits);
     uint64_t vis;
     const uint64_t x = group_resolve(body, body_len, nseg, sm, g, g * kGroupBytes, vis);
-    group_unstage(sm, g, nseg, paths, exits);
+    group_unstage(sm, g, nseg, paths, exits, entries);
     if ((threadIdx.x & 31) == 0) {
         g_exit[g] = x;
         g_vis[g] = vis;
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(kGroupCta) k_group_apply(const uint8_t *__rest
                                                            uint32_t *__restrict__ g_entry,
                                                            uint64_t *__restrict__ g_exit, uint64_t *__restrict__ g_vis,
                                                            unsigned long long *__restrict__ g_claim,
-                                                           uint32_t *__restrict__ changed)
+                                                           uint32_t *__restrict__ changed, uint8_t *__restrict__ entries)
 {
     __shared__ GroupStage stage[kGroupCta / 32];
     const uint64_t g = blockIdx.x * (uint64_t)(kGroupCta / 32) + (threadIdx.x >> 5);
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(kGroupCta) k_group_apply(const uint8_t *__rest
     group_stage(sm, g, nseg, paths, exits);
     uint64_t vis;
     const uint64_t x = group_resolve(body, body_len, nseg, sm, g, e, vis);
-    group_unstage(sm, g, nseg, paths, exits);
+    group_unstage(sm, g, nseg, paths, exits, entries);
     if (lane == 0) {
         g_exit[g] = x;
         g_vis[g] = vis;
@@ -467,7 +471,8 @@ __global__ void __launch_bounds__(kGroupCta) k_group_apply32(const uint8_t *__re
                                                              uint64_t *__restrict__ g_vis,
                                                              unsigned long long *__restrict__ g_claim,
                                                              uint32_t *__restrict__ changed,
-                                                             const uint32_t *__restrict__ prev_changed)
+                                                             const uint32_t *__restrict__ prev_changed,
+                                                             uint8_t *__restrict__ entries)
 {
     __shared__ GroupStage stage[kGroupCta / 32];
     if (prev_changed && *prev_changed == 0)
@@ -515,7 +520,7 @@ __global__ void __launch_bounds__(kGroupCta) k_group_apply32(const uint8_t *__re
         group_stage(sm, gg, nseg, paths, exits);
         uint64_t vis;
         const uint64_t x = group_resolve(body, body_len, nseg, sm, gg, ee, vis);
-        group_unstage(sm, gg, nseg, paths, exits);
+        group_unstage(sm, gg, nseg, paths, exits, entries);
         if (lane == 0) {
             g_exit[gg] = x;
             g_vis[gg] = vis;
@@ -528,63 +533,54 @@ __global__ void __launch_bounds__(kGroupCta) k_group_apply32(const uint8_t *__re
 // the entry of each of its segments; every live segment is then walked from that entry (C): the
 // output bytes of the elements that start in it are summed, and the (speculative) path map is
 // replaced by the exact map of element starts -- what the segment-driven decoder consumes.
-__global__ void __launch_bounds__(kGroupCta) k_group_final(const uint8_t *__restrict__ body, uint64_t body_len,
-                                                           uint64_t nseg, uint64_t ngroup, uint4 *__restrict__ paths,
-                                                           const uint64_t *__restrict__ exits,
-                                                           const uint32_t *__restrict__ g_entry,
-                                                           uint64_t *__restrict__ outlen,
-                                                           uint32_t *__restrict__ status, int open_end)
+__global__ void __launch_bounds__(256) k_group_final(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t nseg,
+                                                     uint64_t ngroup, uint4 *__restrict__ paths,
+                                                     const uint32_t *__restrict__ g_entry,
+                                                     const uint8_t *__restrict__ entries, uint64_t *__restrict__ outlen,
+                                                     uint32_t *__restrict__ status, int open_end)
 {
-    __shared__ GroupStage stage[kGroupCta / 32];
-    const uint64_t g = blockIdx.x * (uint64_t)(kGroupCta / 32) + (threadIdx.x >> 5);
-    if (g >= ngroup)
+    // One thread per segment.  The entry of the segment comes from the last resolution of its group (stored
+    // by group_unstage): the group's final entry always lies on that chain (a group is re-resolved whenever
+    // its entry leaves the chain), so the stored entries hold from the final entry's segment onwards;
+    // segments before it belonged to a speculative prefix and hold nothing.
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= nseg)
         return;
-    const uint32_t lane = threadIdx.x & 31;
-    GroupStage &sm = stage[threadIdx.x >> 5];
+    const uint64_t g = t / kGroup;
     const uint32_t ge = g_entry[g];
-    const uint64_t s0 = g * kGroup;
-    if (ge & kGDead) {
-        for (uint32_t k = lane; k < kGroup; k += 32)
-            if (s0 + k < nseg) {
-                outlen[s0 + k] = 0;
-                paths[s0 + k] = make_uint4(0, 0, 0, 0);
-            }
-        return;
+    const uint32_t k = (uint32_t)(t - g * kGroup);
+    uint32_t en = kDead;
+    if (!(ge & kGDead)) {
+        const uint32_t k0 = ge / kSeg;
+        if (k == k0)
+            en = ge - k0 * kSeg;
+        else if (k > k0)
+            en = entries[t];
     }
-    group_stage(sm, g, nseg, paths, exits);
-    uint64_t vis;
-    (void)group_resolve(body, body_len, nseg, sm, g, g * kGroupBytes + ge, vis);
-    const uint8_t *vbody = body;
-    for (uint32_t k = lane; k < kGroup; k += 32) {
-        const uint64_t t = s0 + k;
-        if (t >= nseg)
-            break;
-        uint64_t sum = 0;
-        Path p;
-        p.clear();
-        const uint32_t en = sm.entry[k];
-        if (!(en & kDead)) {
-            const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
-            uint64_t e = lo + en;
-            while (e < hi) {
-                const Elem el = decode_at<true>(vbody, body_len, e);
-                if (!el.ok || e + el.size > body_len) {
-                    // the element runs past the bytes we have: an error for a whole stream, the
-                    // normal end of a partial one (open_end: the rest has not been uploaded yet)
-                    if (!open_end)
-                        atomicOr(status, SNAPPY_B200_ST_CORRUPT);
-                    break;
-                }
-                if (el.out > kBlock)
-                    atomicOr(status, SNAPPY_B200_ST_FRAMING);
-                p.set((uint32_t)(e - lo));
-                sum += el.out;
-                e += el.size;
+    uint64_t sum = 0;
+    Path p;
+    p.clear();
+    if (!(en & kDead)) {
+        const uint64_t lo = t * kSeg, hi = min(lo + kSeg, body_len);
+        uint64_t e = lo + en;
+        while (e < hi) {
+            const Elem el = decode_at<true>(body, body_len, e);
+            if (!el.ok || e + el.size > body_len) {
+                // the element runs past the bytes we have: an error for a whole stream, the
+                // normal end of a partial one (open_end: the rest has not been uploaded yet)
+                if (!open_end)
+                    atomicOr(status, SNAPPY_B200_ST_CORRUPT);
+                break;
             }
+            if (el.out > kBlock)
+                atomicOr(status, SNAPPY_B200_ST_FRAMING);
+            p.set((uint32_t)(e - lo));
+            sum += el.out;
+            e += el.size;
         }
-        outlen[t] = sum;
-        paths[t] = make_uint4(p.bits[0], p.bits[1], p.bits[2], p.bits[3]);
     }
+    outlen[t] = sum;
+    paths[t] = make_uint4(p.bits[0], p.bits[1], p.bits[2], p.bits[3]);
 }
 
 // Exclusive scan of a u64 array (one entry per 128 stream bytes, so millions of entries): tile
@@ -880,7 +876,7 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
     const unsigned wgrid32 = (unsigned)((ngroup + kGroupCta - 1) / kGroupCta);           // one lane per group
     k_index_spec<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits);
     k_group_init<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.g_exit, w.g_vis,
-                                        w.claim);
+                                        w.claim, w.entry);
     *launches += 2;
     const uint64_t max_rounds = std::min<uint64_t>(ngroup + 2 + kMaxBatch, kMaxRounds);
     const uint32_t *unresolved = nullptr; // flag of the last round run, when nothing proves convergence
@@ -893,11 +889,11 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
             k_group_scatter<<<ggrid, 128, 0, st>>>(body, body_len, ngroup, w.g_entry, w.g_exit, w.claim, prev);
             if (round + k == 0) // the first round moves most groups: one warp each
                 k_group_apply<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry,
-                                                           w.g_exit, w.g_vis, w.claim, w.changed + k);
+                                                           w.g_exit, w.g_vis, w.claim, w.changed + k, w.entry);
             else
                 k_group_apply32<<<wgrid32, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits,
                                                                w.g_entry, w.g_exit, w.g_vis, w.claim, w.changed + k,
-                                                               prev);
+                                                               prev, w.entry);
         }
         *launches += 2 * batch;
         if (fixed_rounds) {
@@ -926,8 +922,8 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
         }
         batch = std::min<uint32_t>(batch * 3, kMaxBatch);
     }
-    k_group_final<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.outlen,
-                                               d_status, open_end);
+    k_group_final<<<grid, 256, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.g_entry, w.entry, w.outlen, d_status,
+                                        open_end);
     const uint64_t ntile = (nseg + kScanTile - 1) / kScanTile;
     k_scan_tile_sums<<<(unsigned)ntile, kScanCta, 0, st>>>(w.outlen, nseg, w.tile_sums);
     k_scan_tiles<<<1, kScanCta, 0, st>>>(w.tile_sums, ntile, w.total);
