@@ -180,6 +180,57 @@ def run_reference_arm(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------ FILE* layer / CLI
+def file_layer_e2e(api, data, c_bytes: int) -> dict:
+    import ctypes as C
+    import shutil
+    d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        src, comp, back = (os.path.join(d, x) for x in ("in.bin", "out.snp", "back.bin"))
+        data.tofile(src)
+        n = data.size
+        libc = C.CDLL(None)
+        libc.fopen.restype = C.c_void_p
+        libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+        libc.fclose.argtypes = [C.c_void_p]
+        L = api.lib()
+        L.snappy_compress.restype = None
+        L.snappy_compress.argtypes = [C.c_void_p, C.c_ulonglong, C.c_void_p]
+        L.snappy_decompress.restype = C.c_int
+        L.snappy_decompress.argtypes = [C.c_void_p, C.c_void_p]
+
+        def call(fn, a, b, *extra):
+            fi, fo = libc.fopen(a.encode(), b"rb"), libc.fopen(b.encode(), b"wb")
+            t0 = time.perf_counter()
+            fn(fi, *extra, fo)
+            libc.fclose(fo)
+            dt = time.perf_counter() - t0
+            libc.fclose(fi)
+            return dt
+
+        call(L.snappy_compress, src, comp, n)  # warm-up (page-locked buffers, module load)
+        t_c = min(call(L.snappy_compress, src, comp, n) for _ in range(2))
+        assert os.path.getsize(comp) == c_bytes, "FILE* layer: stream size differs"
+        call(L.snappy_decompress, comp, back)
+        t_d = min(call(L.snappy_decompress, comp, back) for _ in range(2))
+        assert os.path.getsize(back) == n
+        out = {"bytes": n, "where": "tmpfs (/dev/shm)" if d.startswith("/dev/shm") else d,
+               "dropin_compress_GBs": n / t_c / 1e9, "dropin_decompress_GBs": n / t_d / 1e9,
+               "dropin": "snappy_compress / snappy_decompress on FILE*, in process, warm, fclose included"}
+        t0 = time.perf_counter()
+        subprocess.run([api.CLI_PATH, "-c", src, comp], check=True)
+        t1 = time.perf_counter()
+        subprocess.run([api.CLI_PATH, "-d", comp, back], check=True)
+        t2 = time.perf_counter()
+        import numpy as np
+        assert np.array_equal(np.fromfile(back, np.uint8), data), "CLI round trip failed"
+        out.update({"cli_compress_GBs": n / (t1 - t0) / 1e9, "cli_decompress_GBs": n / (t2 - t1) / 1e9,
+                    "cli": "snappy_b200 -c / -d, one process per call (CUDA start-up and page-locking included)"})
+        return out
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def measured_peak() -> tuple[float, str]:
     try:
@@ -414,6 +465,13 @@ def run_gpu_arm(args) -> None:
         dt_b = e2e(e2e_bst)
         assert got["b"].size == tb["c_bytes"] and torch.equal(h_comp[:tb["c_bytes"]].to(dev), stream_b), "e2e BST stream differs"
 
+    # ---- the drop-in layer end to end: tmpfs file -> file through the reference's own entry points
+    # (snappy_compress / snappy_decompress on FILE*, in process, warm) and through the command line (a new
+    # process per call: CUDA start-up included), wall clock
+    cli = None
+    if rank == 0 and world == 1 and not args.no_cli:
+        cli = file_layer_e2e(api, data.cpu().numpy(), c_bytes)
+
     clocks = sampler.stop() if sampler else None
     td["clocks"] = tc["clocks"] = clocks
 
@@ -495,6 +553,8 @@ def run_gpu_arm(args) -> None:
                 b = tb["base"]
                 line["bst"]["cpu_baseline"] = {"value": b["compress_value"], "unit": "GB/s", "cores": b["cores"],
                                                "kind": b["kind"], "sample": b["sample"], "ratio": b["ratio"]}
+        if cli is not None:
+            line["cli_e2e"] = cli
         if base is not None:
             line["cpu_baseline"] = base
         print(json.dumps(line), flush=True)
@@ -512,6 +572,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bst", action="store_true", help="skip the configs[3] (BST path) leg")
+    ap.add_argument("--no-cli", action="store_true", help="skip the FILE* / command-line end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -186,6 +186,10 @@ int snappy_b200_decompress_host_indexed_multi(const void *stream, uint64_t strea
  * drop-in calls (caller opens and closes).                                                */
 int snappy_b200_compress_file_indexed(FILE *in, unsigned long long input_size, int mode, FILE *out, FILE *index_out);
 int snappy_b200_decompress_file_indexed(FILE *in, FILE *index_in, FILE *out);
+/* FILE* -> FILE* decompression with the stream and the output device-resident and only a ring of three
+ * page-locked 32 MiB chunks on the host (fread -> H2D, K0 + decode, D2H -> fwrite).  Returns 1 (nothing read,
+ * nothing written) when `in` is not seekable or the data does not fit the device: decode whole buffers then. */
+int snappy_b200_decompress_file(FILE *in, FILE *out);
 /* Releases the cached device/pinned buffers of the host-buffer API. */
 void snappy_b200_release(void);
 /* Page-locked host memory for the buffers handed to the host-buffer API (what the reference's

@@ -71,6 +71,7 @@ SIGNATURES = {
     "snappy_b200_decompress_host_multi": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]),
     "snappy_b200_decompress_host_indexed_multi": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, _u8p, C.c_uint64,
                                                             C.POINTER(C.c_uint64), C.c_int]),
+    "snappy_b200_decompress_file": (C.c_int, [C.c_void_p, C.c_void_p]),
     "snappy_b200_compress_file_indexed": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p]),
     "snappy_b200_decompress_file_indexed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snappy_b200_release": (None, []),

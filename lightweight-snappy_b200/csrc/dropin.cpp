@@ -30,6 +30,45 @@ namespace {
 
 int io_fail(const char *what) { return sb200::fail_msg(SNAPPY_B200_ERR_IO, what); }
 
+// Page-locking is expensive (measured on the B200 box: 85 ms for 64 MiB, 410 ms for 1 GiB), so buffers that
+// are given back are kept for the next call of the process instead of being unlocked (up to 1 GiB in total).
+struct PinnedPool {
+    struct Item {
+        void *p;
+        size_t cap;
+    };
+    std::mutex mu;
+    std::vector<Item> items;
+    size_t bytes = 0;
+    void *take(size_t want, size_t &cap)
+    {
+        std::lock_guard<std::mutex> l(mu);
+        for (size_t i = 0; i < items.size(); ++i)
+            if (items[i].cap >= want && items[i].cap <= 2 * want + (1u << 20)) {
+                void *p = items[i].p;
+                cap = items[i].cap;
+                bytes -= cap;
+                items.erase(items.begin() + (long)i);
+                return p;
+            }
+        return nullptr;
+    }
+    bool give(void *p, size_t cap)
+    {
+        std::lock_guard<std::mutex> l(mu);
+        if (bytes + cap > (1ull << 30))
+            return false;
+        items.push_back({p, cap});
+        bytes += cap;
+        return true;
+    }
+};
+PinnedPool &pinned_pool()
+{
+    static PinnedPool *pool = new PinnedPool; // (never destroyed: the CUDA runtime may be gone by then)
+    return *pool;
+}
+
 // A growable byte buffer in page-locked host memory (plain malloc when no device is usable, so
 // that error paths still work): what the reference's Buffer / IO_utils allocations become.
 struct PinnedBuf {
@@ -40,10 +79,12 @@ struct PinnedBuf {
     void drop()
     {
         if (p) {
-            if (pinned)
-                snappy_b200_host_free(p);
-            else
+            if (pinned) {
+                if (!pinned_pool().give(p, cap))
+                    snappy_b200_host_free(p);
+            } else {
                 free(p);
+            }
         }
         p = nullptr;
         cap = n = 0;
@@ -52,7 +93,10 @@ struct PinnedBuf {
     {
         if (want <= cap)
             return true;
-        void *q = snappy_b200_host_alloc(want);
+        size_t got_cap = want;
+        void *q = pinned_pool().take(want, got_cap);
+        if (!q)
+            q = snappy_b200_host_alloc(want);
         bool qp = q != nullptr;
         if (!q)
             q = malloc(want);
@@ -63,7 +107,7 @@ struct PinnedBuf {
         const size_t keep = n;
         drop();
         p = static_cast<uint8_t *>(q);
-        cap = want;
+        cap = qp ? got_cap : want;
         n = keep;
         pinned = qp;
         return true;
@@ -97,7 +141,7 @@ const char kIndexMagic[8] = {'S', 'N', 'P', 'I', 'D', 'X', '1', 0};
 
 // The streaming compressor behind snappy_compress / snappy_compress_bst.  The reference works through the file
 // 64 KiB at a time (src/snappy_compression.c:210-213, :419-425); here the unit is a chunk of whole blocks
-// (256 MiB per device in use): a reader thread fills page-locked input buffers, the calling thread runs the
+// (64 MiB per device in use): a reader thread fills page-locked input buffers, the calling thread runs the
 // GPU pipeline on one chunk while the next is being read, a writer thread appends the finished chunks.
 // Three chunks are in flight, so page-locked memory is bounded by the chunk size, not by the file size.
 struct ChunkQueue { // hands slot numbers from one thread to the next
@@ -124,7 +168,7 @@ struct ChunkQueue { // hands slot numbers from one thread to the next
 
 uint64_t stream_chunk_bytes(unsigned long long declared)
 {
-    uint64_t mib = 256;
+    uint64_t mib = 64;
     if (const char *v = getenv("SNAPPY_B200_FILE_CHUNK_MIB"))
         mib = (uint64_t)std::max(1ll, atoll(v));
     uint64_t dev = 1;
@@ -323,7 +367,14 @@ int snappy_decompress(FILE *file_input, FILE *file_decompressed)
 {
     PinnedBuf stream, out;
     sb200::clear_error();
-    if (!file_input || !file_decompressed || !read_all(file_input, 0, stream))
+    if (!file_input || !file_decompressed)
+        return io_fail("null FILE*");
+    // the streamed path (stream and output device-resident, three page-locked chunks on the host) ...
+    const int streamed = snappy_b200_decompress_file(file_input, file_decompressed);
+    if (streamed != 1)
+        return streamed;
+    // ... or, for a pipe or a stream too large for one device, whole host buffers and the piecewise pipeline
+    if (!read_all(file_input, 0, stream))
         return io_fail("reading the compressed stream failed");
     uint64_t total = 0;
     int rc = snappy_b200_uncompressed_length(stream.data(), stream.size(), &total);

@@ -101,6 +101,27 @@ struct HostCtx {
     size_t cap[kBufs] = {};
     uint64_t *h_small = nullptr; // pinned scratch for small read-backs
     cudaEvent_t ev[32] = {};
+    static constexpr int kFileSlots = 3;
+    uint8_t *h_file[kFileSlots] = {}; // page-locked chunk ring of the FILE* decompressor
+    size_t h_file_cap = 0;
+    cudaError_t need_file_ring(size_t bytes)
+    {
+        if (h_file_cap >= bytes)
+            return cudaSuccess;
+        for (auto &p : h_file) {
+            if (p)
+                cudaFreeHost(p);
+            p = nullptr;
+        }
+        h_file_cap = 0;
+        for (auto &p : h_file) {
+            const cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&p), bytes, cudaHostAllocDefault);
+            if (e != cudaSuccess)
+                return e;
+        }
+        h_file_cap = bytes;
+        return cudaSuccess;
+    }
 
     cudaError_t need(int i, size_t bytes)
     {
@@ -148,6 +169,12 @@ struct HostCtx {
         if (h_small)
             cudaFreeHost(h_small);
         h_small = nullptr;
+        for (auto &p : h_file) {
+            if (p)
+                cudaFreeHost(p);
+            p = nullptr;
+        }
+        h_file_cap = 0;
         for (auto &x : ev) {
             if (x)
                 cudaEventDestroy(x);
@@ -657,6 +684,121 @@ int snappy_b200_decompress_host(const void *stream, uint64_t stream_bytes, void 
         return rc;
     clear_error();
     return decompress_host_general(stream, stream_bytes, out, out_bytes); // (all arguments were checked above)
+}
+
+// ---- FILE* -> FILE* decompression (what snappy_decompress, src/snappy_decompression.c:345-363, becomes).
+// The reference reads the stream through a 128 KiB window and holds the whole output in memory until one
+// final fwrite (:349, :359).  Here the whole stream and the whole output live in DEVICE memory; the host
+// only ever holds a ring of three page-locked chunks (32 MiB each, kept for the life of the process):
+//   fread chunk -> H2D   (the upload of chunk i overlaps the fread of chunk i+1)
+//   K0 + block decode on the device-resident stream (or the general decoder for unframed streams)
+//   D2H chunk -> fwrite  (the download of chunk i+1 overlaps the fwrite of chunk i)
+// Returns 1 when the stream cannot be handled this way (not seekable, or too large for the device): the
+// caller then falls back to whole-buffer decoding.
+int snappy_b200_decompress_file(FILE *in, FILE *out)
+{
+    clear_error();
+    if (!in || !out)
+        return fail_msg(SNAPPY_B200_ERR_IO, "null FILE*");
+    const long at = ftell(in);
+    if (at < 0 || fseek(in, 0, SEEK_END) != 0)
+        return 1;
+    const long end = ftell(in);
+    if (end < at || fseek(in, at, SEEK_SET) != 0)
+        return 1;
+    const uint64_t L = (uint64_t)(end - at);
+    if (L == 0)
+        return SNAPPY_B200_OK; // the reference's empty stream
+    uint8_t head[16];
+    const size_t got_head = fread(head, 1, std::min<uint64_t>(L, sizeof head), in);
+    if (fseek(in, at, SEEK_SET) != 0)
+        return fail_msg(SNAPPY_B200_ERR_IO, "seek failed");
+    uint64_t total = 0;
+    const unsigned hdr = host_varint_decode(head, got_head, &total);
+    if (!hdr)
+        return fail_msg(SNAPPY_B200_ERR_CORRUPT, "bad varint preamble");
+    if (total == 0)
+        return L == hdr ? SNAPPY_B200_OK : fail_msg(SNAPPY_B200_ERR_CORRUPT, "trailing bytes after an empty stream");
+    if (L > max_compressed(total) + 16)
+        return fail_msg(SNAPPY_B200_ERR_CORRUPT, "stream is longer than any encoding of its declared length");
+    if (total >= (1ull << 40))
+        return 1;
+    HostCtx &g_ctx = current_ctx();
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    CU(g_ctx.init(), "context init");
+    constexpr size_t kFileChunk = 32u << 20;
+    const uint64_t nb = (total + kBlock - 1) / kBlock;
+    if (g_ctx.need(0, L + 64) != cudaSuccess || g_ctx.need(1, total) != cudaSuccess ||
+        g_ctx.need(2, index_workspace_bytes(L)) != cudaSuccess || g_ctx.need(4, (nb + 2) * 8) != cudaSuccess ||
+        g_ctx.need(6, 256) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 1; // does not fit this device: the piecewise host path needs far less device memory
+    }
+    CU(g_ctx.need_file_ring(kFileChunk), "cudaHostAlloc");
+    uint8_t *d_stream = static_cast<uint8_t *>(g_ctx.buf[0]);
+    uint8_t *d_out = static_cast<uint8_t *>(g_ctx.buf[1]);
+    uint64_t *d_offs = static_cast<uint64_t *>(g_ctx.buf[4]);
+    uint32_t *d_status = static_cast<uint32_t *>(g_ctx.buf[6]);
+    cudaEvent_t *ev = g_ctx.ev + 21; // three slots
+    // ---- up
+    uint64_t k = 0;
+    for (uint64_t off = 0; off < L; off += kFileChunk, ++k) {
+        const int slot = (int)(k % HostCtx::kFileSlots);
+        const uint64_t len = std::min<uint64_t>(kFileChunk, L - off);
+        if (k >= (uint64_t)HostCtx::kFileSlots)
+            CU(cudaEventSynchronize(ev[slot]), "H2D copy");
+        if (fread(g_ctx.h_file[slot], 1, len, in) != len) {
+            cudaDeviceSynchronize();
+            return fail_msg(SNAPPY_B200_ERR_IO, "reading the compressed stream failed");
+        }
+        CU(cudaMemcpyAsync(d_stream + off, g_ctx.h_file[slot], len, cudaMemcpyHostToDevice, g_ctx.s_run), "H2D copy");
+        CU(cudaEventRecord(ev[slot], g_ctx.s_run), "event record");
+    }
+    // ---- decode
+    uint64_t launches = 0;
+    CU(cudaMemsetAsync(d_status, 0, 4, g_ctx.s_run), "memset");
+    CU(run_index(d_stream, L, hdr, total, d_offs, d_status, g_ctx.buf[2], g_ctx.s_run, &launches, false, 0), "index launch");
+    CU(launch_decode_seg(d_stream, hdr, d_offs, index_starts(g_ctx.buf[2], L), index_outoff(g_ctx.buf[2], L), nb, total,
+                         d_out, d_status, 0, g_ctx.s_run, &launches),
+       "decode launch");
+    CU(peek_u32(reinterpret_cast<uint32_t *>(g_ctx.h_small + 1), d_status, 1, g_ctx.s_run), "read-back");
+    CU(cudaStreamSynchronize(g_ctx.s_run), "decode");
+    uint32_t status = (uint32_t)g_ctx.h_small[1];
+    if (status & SNAPPY_B200_ST_FRAMING) { // valid raw Snappy, but not framed in 64 KiB blocks: the general decoder
+        CU(cudaMemsetAsync(d_status, 0, 4, g_ctx.s_run), "memset");
+        CU(launch_decode_sequential(d_stream, L, hdr, total, d_out, d_status, g_ctx.s_run, &launches), "decode launch");
+        CU(peek_u32(reinterpret_cast<uint32_t *>(g_ctx.h_small + 1), d_status, 1, g_ctx.s_run), "read-back");
+        CU(cudaStreamSynchronize(g_ctx.s_run), "decode");
+        status = (uint32_t)g_ctx.h_small[1];
+    }
+    add_launches(launches);
+    if (status)
+        return status_error(status);
+    // ---- down
+    const uint64_t n_chunks = (total + kFileChunk - 1) / kFileChunk;
+    auto issue_down = [&](uint64_t c) -> cudaError_t {
+        const int slot = (int)(c % HostCtx::kFileSlots);
+        const uint64_t off = c * kFileChunk, len = std::min<uint64_t>(kFileChunk, total - off);
+        cudaError_t e = cudaMemcpyAsync(g_ctx.h_file[slot], d_out + off, len, cudaMemcpyDeviceToHost, g_ctx.s_down);
+        if (e == cudaSuccess)
+            e = cudaEventRecord(ev[slot], g_ctx.s_down);
+        return e;
+    };
+    CU(issue_down(0), "D2H copy");
+    if (n_chunks > 1)
+        CU(issue_down(1), "D2H copy");
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        const int slot = (int)(c % HostCtx::kFileSlots);
+        const uint64_t off = c * kFileChunk, len = std::min<uint64_t>(kFileChunk, total - off);
+        CU(cudaEventSynchronize(ev[slot]), "D2H copy");
+        if (c + 2 < n_chunks) // (its slot was written out two chunks ago)
+            CU(issue_down(c + 2), "D2H copy");
+        if (fwrite(g_ctx.h_file[slot], 1, len, out) != len) {
+            cudaDeviceSynchronize();
+            return fail_msg(SNAPPY_B200_ERR_IO, "short write of the output");
+        }
+    }
+    return SNAPPY_B200_OK;
 }
 
 // ---- decode with the side index: no K0.  The stream goes up in pieces cut at block boundaries
