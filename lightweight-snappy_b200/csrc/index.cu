@@ -66,30 +66,27 @@ struct Elem {
 template <bool LDG = true>
 __device__ __forceinline__ Elem decode_at(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t e)
 {
+    // Written with selects instead of branches: the threads of a warp walk different segments, and every
+    // branch on the element kind would split the warp (the walks are issue bound: k_index_spec ran at 91 %
+    // issue utilisation with 14 of 32 lanes active).  Only the 1..4 length bytes of a long literal, which are
+    // rare, sit behind a branch.
     Elem r;
     const uint32_t tag = LDG ? __ldg(body + e) : body[e];
-    const uint32_t type = tag & 3u;
-    uint32_t extra; // header bytes after the tag
-    if (type == 0) {
-        const uint32_t m = tag >> 2;
-        extra = m >= 60 ? m - 59 : 0;
-    } else {
-        extra = type == 1 ? 1 : (type == 2 ? 2 : 4);
-    }
+    const uint32_t type = tag & 3u, m = tag >> 2;
+    const bool lit = type == 0;
+    const bool longlit = lit && m >= 60;
+    const uint32_t extra = lit ? (longlit ? m - 59u : 0u) : ((0x4210u >> (type * 4u)) & 0xfu); // header bytes after the tag
     r.ok = e + 1 + extra <= body_len;
-    uint32_t raw = 0;
-    if (type == 0 && extra && r.ok) {
-        for (uint32_t k = 0; k < extra; ++k)
-            raw |= (uint32_t)(LDG ? __ldg(body + e + 1 + k) : body[e + 1 + k]) << (8 * k);
+    uint32_t raw = m;
+    if (longlit) {
+        raw = 0;
+        if (r.ok)
+            for (uint32_t k = 0; k < extra; ++k)
+                raw |= (uint32_t)(LDG ? __ldg(body + e + 1 + k) : body[e + 1 + k]) << (8 * k);
     }
-    if (type == 0) {
-        const uint64_t len = (uint64_t)((tag >> 2) >= 60 ? raw : (tag >> 2)) + 1;
-        r.size = 1 + extra + len;
-        r.out = len;
-    } else {
-        r.size = 1 + extra;
-        r.out = type == 1 ? ((tag >> 2) & 7u) + 4 : (tag >> 2) + 1;
-    }
+    const uint64_t len = lit ? (uint64_t)raw + 1 : 0;      // payload bytes that follow the header
+    r.size = 1 + extra + len;
+    r.out = lit ? len : (uint64_t)(type == 1 ? (m & 7u) + 4u : m + 1u);
     return r;
 }
 
@@ -98,18 +95,16 @@ struct Path {
     __device__ __forceinline__ void clear() { bits[0] = bits[1] = bits[2] = bits[3] = 0; }
     __device__ __forceinline__ void set(uint32_t i)
     {
-#pragma unroll
-        for (int w = 0; w < 4; ++w)
-            if ((i >> 5) == (uint32_t)w)
-                bits[w] |= 1u << (i & 31);
+        const uint32_t b = 1u << (i & 31), w = i >> 5;
+        bits[0] |= w == 0 ? b : 0u;
+        bits[1] |= w == 1 ? b : 0u;
+        bits[2] |= w == 2 ? b : 0u;
+        bits[3] |= w == 3 ? b : 0u;
     }
     __device__ __forceinline__ bool test(uint32_t i) const
     {
-        uint32_t v = 0;
-#pragma unroll
-        for (int w = 0; w < 4; ++w)
-            if ((i >> 5) == (uint32_t)w)
-                v = bits[w];
+        const uint32_t w = i >> 5;
+        const uint32_t v = w == 0 ? bits[0] : (w == 1 ? bits[1] : (w == 2 ? bits[2] : bits[3]));
         return (v >> (i & 31)) & 1u;
     }
 };
