@@ -75,6 +75,8 @@ def main() -> None:
     codec.decompress(ws, ws.numel(), 3, warm.numel(), out, idx)
     codec.check_status()
 
+    from bench import ClockSampler  # nvidia-smi clocks / throttle reasons during the measured section
+    sampler = ClockSampler(local) if rank == 0 else None
     ev = lambda: torch.cuda.Event(enable_timing=True)
     t_comp = t_decomp = 0.0
     c_total = 0
@@ -138,8 +140,10 @@ def main() -> None:
     total_checked = red(float(checked), R.SUM if R else None)
     ok = red(1.0 if sum_in == sum_out else 0.0, R.MIN if R else None)
     u = n_blocks * BLOCK
+    clocks = sampler.stop() if sampler else None
     if rank == 0:
         print(json.dumps({
+            "clocks": clocks,
             "config": f"{args.gib:g} GiB batch = {n_blocks} independent 64 KiB blocks (mixed corpus), "
                       f"{world} GPU(s), block ranges per rank, sub-batches of {sub_bytes / GIB:g} GiB, device-resident",
             "n_gpus": world, "mode": "hash" if args.mode == 0 else "bst",
