@@ -475,6 +475,17 @@ def run_gpu_arm(args) -> None:
     clocks = sampler.stop() if sampler else None
     td["clocks"] = tc["clocks"] = clocks
 
+    # ---- BASELINE configs[4]: the 64 GiB batch of independent blocks, block ranges over the ranks (STRONG
+    # scaling: 64 / N GiB per GPU), device-resident 4 GiB sub-batches, compress then index-less decompress,
+    # 1 % of the blocks checked against the oracle, whole-batch checksum (tools/batch64.py)
+    batch = None
+    if not args.no_batch64:
+        del h_stream, h_data, h_out, h_comp, out, data
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import batch64
+        batch = batch64.run(argparse.Namespace(gib=args.batch_gib, sub_gib=4.0, sample=0.01, mode=0))
+
     # ---- aggregate over ranks
     total_u = sum_over_ranks(float(n))
     total_c = sum_over_ranks(float(c_bytes))
@@ -555,6 +566,9 @@ def run_gpu_arm(args) -> None:
                                                "kind": b["kind"], "sample": b["sample"], "ratio": b["ratio"]}
         if cli is not None:
             line["cli_e2e"] = cli
+        if batch is not None:
+            batch["scaling"] = "strong"
+            line["batch64"] = batch
         if base is not None:
             line["cpu_baseline"] = base
         print(json.dumps(line), flush=True)
@@ -573,6 +587,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bst", action="store_true", help="skip the configs[3] (BST path) leg")
     ap.add_argument("--no-cli", action="store_true", help="skip the FILE* / command-line end-to-end leg")
+    ap.add_argument("--no-batch64", action="store_true", help="skip the configs[4] leg (64 GiB batch, strong scaling)")
+    ap.add_argument("--batch-gib", type=float, default=64.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

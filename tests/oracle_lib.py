@@ -27,7 +27,9 @@ _u8p = C.POINTER(C.c_uint8)
 def build(ref: bool = True) -> None:
     """Compile oracle/ (and oracle/_ref when /root/reference is present)."""
     targets = ["all"] + (["ref"] if ref else [])
-    subprocess.run(["make", "-s", "-C", ORACLE_DIR] + targets, check=True)
+    import sys
+    # (make's chatter goes to stderr: bench.py's stdout is one JSON line)
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR] + targets, check=True, stdout=sys.stderr)
 
 
 def _as_u8(buf) -> np.ndarray:

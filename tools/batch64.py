@@ -37,7 +37,14 @@ def main() -> None:
     ap.add_argument("--sample", type=float, default=0.01, help="fraction of blocks checked against the oracle")
     ap.add_argument("--mode", type=int, default=0)
     args = ap.parse_args()
+    res = run(args, own_process_group=True)
+    if res is not None:
+        print(json.dumps(res), flush=True)
 
+
+def run(args, own_process_group: bool = False, sample_clocks: bool = True):
+    """The whole sweep step for this rank; returns the result dict on rank 0 (None elsewhere).  bench.py calls
+    it with its own process group already up (own_process_group=False)."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -50,12 +57,13 @@ def main() -> None:
         raise SystemExit("needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and own_process_group:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     import oracle_lib  # tests/oracle_lib.py: the checker, never the thing measured
-    oracle_lib.build()
+    if not os.path.exists(oracle_lib.ORACLE_SO):
+        oracle_lib.build(ref=False)
     orc = oracle_lib.Oracle()
 
     n_blocks = int(args.gib * GIB) // BLOCK
@@ -76,7 +84,7 @@ def main() -> None:
     codec.check_status()
 
     from bench import ClockSampler  # nvidia-smi clocks / throttle reasons during the measured section
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and sample_clocks else None
     ev = lambda: torch.cuda.Event(enable_timing=True)
     t_comp = t_decomp = 0.0
     c_total = 0
@@ -141,8 +149,9 @@ def main() -> None:
     ok = red(1.0 if sum_in == sum_out else 0.0, R.MIN if R else None)
     u = n_blocks * BLOCK
     clocks = sampler.stop() if sampler else None
+    result = None
     if rank == 0:
-        print(json.dumps({
+        result = ({
             "clocks": clocks,
             "config": f"{args.gib:g} GiB batch = {n_blocks} independent 64 KiB blocks (mixed corpus), "
                       f"{world} GPU(s), block ranges per rank, sub-batches of {sub_bytes / GIB:g} GiB, device-resident",
@@ -152,9 +161,10 @@ def main() -> None:
             "oracle_checked_blocks": int(total_checked), "oracle_checked_fraction": total_checked / n_blocks,
             "checksum_ok": bool(ok), "roundtrip_ok": True,
             "timing": "sum over sub-batches of the CUDA-event span around the codec call, max over ranks",
-        }), flush=True)
-    if world > 1:
+        })
+    if world > 1 and own_process_group:
         dist.destroy_process_group()
+    return result
 
 
 if __name__ == "__main__":
