@@ -177,7 +177,7 @@ def run_reference_arm(args) -> None:
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "compress": {"value": base["compress_value"], "unit": "GB/s"},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ FILE* layer / CLI
@@ -571,12 +571,31 @@ def run_gpu_arm(args) -> None:
             line["batch64"] = batch
         if base is not None:
             line["cpu_baseline"] = base
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE line on stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner, make)
+    # is sent to stderr by pointing file descriptor 1 at stderr and keeping a private handle to the real stdout
+    global _REAL_STDOUT
+    try:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    except OSError:
+        _REAL_STDOUT = None
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
