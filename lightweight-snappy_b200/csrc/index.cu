@@ -876,6 +876,9 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
     const uint64_t max_rounds = std::min<uint64_t>(ngroup + 2 + kMaxBatch, kMaxRounds);
     const uint32_t *unresolved = nullptr; // flag of the last round run, when nothing proves convergence
     uint32_t batch = fixed_rounds ? std::min<uint32_t>(fixed_rounds, kMaxBatch) : 16;
+    // a chain over ngroup groups is resolved after at most ngroup rounds (one more shows that nothing moves):
+    // small streams do not pay for a full batch of launches
+    batch = (uint32_t)std::min<uint64_t>(batch, ngroup + 1);
     for (uint64_t round = 0;;) {
         if ((e = cudaMemsetAsync(w.changed, 0, 4 * kMaxBatch, st)) != cudaSuccess)
             return e;
