@@ -237,16 +237,18 @@ __global__ void __launch_bounds__(64, MINB) k_decode_seg(const uint8_t *__restri
                                                          const uint64_t *__restrict__ offsets,
                                                          const uint4 *__restrict__ starts, uint64_t total_out,
                                                          uint8_t *out_base, uint32_t *__restrict__ status,
-                                                         uint64_t n_blocks, uint64_t blk_base)
+                                                         uint64_t n_blocks, uint64_t blk_base,
+                                                         const uint32_t *__restrict__ order)
 {
     __shared__ SegSmem sm2[2];
     SegSmem &sm = sm2[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t blk = blockIdx.x * 2ull + (threadIdx.x >> 5);
-    if (blk >= n_blocks)
+    const uint64_t slot = blockIdx.x * 2ull + (threadIdx.x >> 5);
+    if (slot >= n_blocks)
         return;
     if (*reinterpret_cast<volatile uint32_t *>(status) != 0)
         return; // K0 rejected the stream: its maps are not trustworthy
+    const uint64_t blk = order ? order[slot] : slot; // longest blocks first (k_block_order)
     const uint64_t c0 = offsets[blk], c1 = offsets[blk + 1];
     const uint64_t stream_bytes = offsets[n_blocks];
     if (c1 <= c0 || c0 < body_offset || c1 > stream_bytes || c1 - c0 > 2u * kBlock) {
@@ -605,6 +607,34 @@ cudaError_t launch_decode(const uint8_t *d_stream, const uint64_t *d_offsets, ui
     return cudaGetLastError();
 }
 
+// A block is one serial chain (about 2 ms for a text block, 1.5 ms for a low-entropy one, nothing for a block
+// that k_copy_literal_blocks has moved), and 1 GiB is fewer than two waves of them: started in stream order the
+// last wave ends with a few long blocks on an otherwise idle GPU.  The blocks are therefore handed out longest
+// first, by compressed size (counting sort into 1 KiB classes, one CTA).
+__global__ void __launch_bounds__(1024) k_block_order(const uint64_t *__restrict__ offsets, uint64_t n_blocks,
+                                                      const uint32_t *__restrict__ status, uint32_t *__restrict__ order)
+{
+    __shared__ uint32_t cnt[64], base[64];
+    if (*reinterpret_cast<const volatile uint32_t *>(status) != 0)
+        return; // (k_decode_seg returns before it reads `order`)
+    if (threadIdx.x < 64)
+        cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t b = threadIdx.x; b < n_blocks; b += blockDim.x)
+        atomicAdd(&cnt[min((uint64_t)63, (offsets[b + 1] - offsets[b]) >> 10)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t pos = 0;
+        for (int k = 63; k >= 0; --k) {
+            base[k] = pos;
+            pos += cnt[k];
+        }
+    }
+    __syncthreads();
+    for (uint64_t b = threadIdx.x; b < n_blocks; b += blockDim.x)
+        order[atomicAdd(&base[min((uint64_t)63, (offsets[b + 1] - offsets[b]) >> 10)], 1u)] = (uint32_t)b;
+}
+
 cudaError_t launch_decode_tile(const uint8_t *, uint64_t, const uint64_t *, const uint4 *, const uint64_t *, uint64_t,
                                uint64_t, uint8_t *, uint32_t *, uint64_t, cudaStream_t, uint64_t *); // decode_tile.cu
 
@@ -652,10 +682,19 @@ cudaError_t launch_decode_seg(const uint8_t *d_stream, uint64_t body_offset, con
                                                launches);
     if (e != cudaSuccess)
         return e;
+    // The order array lives in the memory of K0's per-segment output offsets, which this decoder does not need
+    // (8 bytes per 128 stream bytes; a 64 KiB block is at least 2 KiB of stream, so it always fits).
+    static const bool in_order = getenv("SNAPPY_B200_DECODE_IN_ORDER") != nullptr; // A/B: blocks in stream order
+    uint32_t *d_order = nullptr;
+    if (!in_order && d_outoff && n_blocks > 1) {
+        d_order = reinterpret_cast<uint32_t *>(const_cast<uint64_t *>(d_outoff));
+        k_block_order<<<1, 1024, 0, st>>>(d_offsets, n_blocks, d_status, d_order);
+        *launches += 1;
+    }
     // two blocks (warps) per CTA and a 48-register cap: 40 warps per SM instead of the 32 that one-warp
     // CTAs allow (measured: 64 registers / 32 warps 6.92, 48 / 40 6.72, 40 / 48 6.84 ms per GiB, K0 included)
     k_decode_seg<20><<<(unsigned)((n_blocks + 1) / 2), 64, 0, st>>>(d_stream, body_offset, d_offsets, d_starts, total_out,
-                                                                    d_out, d_status, n_blocks, blk_base);
+                                                                    d_out, d_status, n_blocks, blk_base, d_order);
     *launches += 1;
     return cudaGetLastError();
 }
