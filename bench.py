@@ -338,7 +338,8 @@ def run_gpu_arm(args) -> None:
         clocks = None
         total_ms = t_start.elapsed_time(t_end)
         try:
-            kern_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+            # (median of the per-step spans: a host hiccup between two launches of one step is not kernel time)
+            kern_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
         except (ValueError, RuntimeError):  # this step does not bracket a kernel of its own
             kern_ms = None
         return {"total_ms": max_over_ranks(total_ms), "kernel_ms": kern_ms, "clocks": clocks,
