@@ -42,6 +42,7 @@
 //                      reported as SNAPPY_B200_ST_FRAMING.
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(kGroupCta) k_group_init(const uint8_t *__restr
                                                           uint32_t *__restrict__ g_entry, uint64_t *__restrict__ g_exit,
                                                           uint64_t *__restrict__ g_vis,
                                                           unsigned long long *__restrict__ g_claim,
-                                                          uint8_t *__restrict__ entries)
+                                                          uint8_t *__restrict__ entries, int getenv_runup)
 {
     __shared__ GroupStage stage[kGroupCta / 32];
     const uint64_t g = blockIdx.x * (uint64_t)(kGroupCta / 32) + (threadIdx.x >> 5);
@@ -319,13 +320,44 @@ __global__ void __launch_bounds__(kGroupCta) k_group_init(const uint8_t *__restr
         return;
     GroupStage &sm = stage[threadIdx.x >> 5];
     group_stage(sm, g, nseg, paths, exits);
+    // First belief about where the chain enters this group.  "At its first byte" is right one time in four
+    // on text; the speculative walks of the segments just before the group are a free run-up: follow their
+    // exits (exit of segment s, landing on the recorded path of the segment it falls in, that segment's exit,
+    // ...) from up to three segments back into the group.  Every hop that lands on a recorded path halves the
+    // chance that the walk is still off the true chain.  Only table look-ups, no tag walk; any value read here
+    // is a guess that the relaxation corrects (a neighbour may be rewriting its records meanwhile).
+    uint64_t e0 = g * kGroupBytes;
+    if (g > 0 && getenv_runup) {
+        const uint64_t g_lo = g * kGroupBytes, g_hi = min(g_lo + kGroupBytes, body_len);
+        const uint64_t s_last = g * kGroup - 1;
+        for (int back = 2; back >= 0; --back) {
+            if (s_last < (uint64_t)back)
+                continue;
+            uint64_t x = exits[s_last - back];
+            bool ok = true;
+            for (int hop = 0; ok && x < g_lo && hop < 4; ++hop) {
+                const uint64_t sx = x / kSeg;
+                const uint4 pv = paths[sx];
+                Path p;
+                p.bits[0] = pv.x, p.bits[1] = pv.y, p.bits[2] = pv.z, p.bits[3] = pv.w;
+                ok = p.test((uint32_t)(x - sx * kSeg));
+                if (ok)
+                    x = exits[sx];
+            }
+            if (ok && x >= g_lo) {
+                if (x < g_hi)
+                    e0 = x;
+                break; // (a chain that jumps over the whole group keeps the default)
+            }
+        }
+    }
     uint64_t vis;
-    const uint64_t x = group_resolve(body, body_len, nseg, sm, g, g * kGroupBytes, vis);
+    const uint64_t x = group_resolve(body, body_len, nseg, sm, g, e0, vis);
     group_unstage(sm, g, nseg, paths, exits, entries);
     if ((threadIdx.x & 31) == 0) {
         g_exit[g] = x;
         g_vis[g] = vis;
-        g_entry[g] = 0;
+        g_entry[g] = (uint32_t)(e0 - g * kGroupBytes);
         g_claim[g] = kNone;
     }
 }
@@ -871,7 +903,7 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
     const unsigned wgrid32 = (unsigned)((ngroup + kGroupCta - 1) / kGroupCta);           // one lane per group
     k_index_spec<<<grid, 256, 0, st>>>(body, body_len, nseg, w.paths, w.exits);
     k_group_init<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry, w.g_exit, w.g_vis,
-                                        w.claim, w.entry);
+                                        w.claim, w.entry, getenv("SNAPPY_B200_K0_NO_RUNUP") == nullptr);
     *launches += 2;
     const uint64_t max_rounds = std::min<uint64_t>(ngroup + 2 + kMaxBatch, kMaxRounds);
     const uint32_t *unresolved = nullptr; // flag of the last round run, when nothing proves convergence
