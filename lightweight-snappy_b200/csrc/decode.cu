@@ -649,7 +649,8 @@ cudaError_t launch_copy_literal_blocks(const uint8_t *, uint64_t, const uint64_t
 
 // Decoder for the maps K0 leaves behind.  The product path is the warp-per-block, segment-driven decoder
 // above (k_decode_seg) preceded by k_copy_literal_blocks, which moves the blocks that are a single literal
-// (incompressible data) with plain 16-byte vector copies.  Three other designs were built and measured in
+// (incompressible data) with plain 16-byte vector copies; inputs of at most 32 blocks go to the tile decoder
+// (k_decode_tile), whose eight warps per block give the lower latency.  Three other designs were built and measured in
 // round 2 and lost (1 GiB mixed corpus: seg 4.1 ms; profiles/r02_*): SNAPPY_B200_DECODER=tile selects the
 // one-CTA-per-block decoder with the whole 64 KiB block in shared memory (decode_tile.cu, 32 ms), =win the
 // sub-warp-group-per-block decoder with a sliding shared-memory window (decode_win.cu, 9.3 ms), =lane the
@@ -664,10 +665,16 @@ cudaError_t launch_decode_seg(const uint8_t *d_stream, uint64_t body_offset, con
         return cudaSuccess;
     if (n_blocks > 0x7fffffffull)
         return cudaErrorInvalidValue;
-    static const char which = [] {
+    static const char which_env = [] {
         const char *v = getenv("SNAPPY_B200_DECODER");
-        return v ? v[0] : 's';
+        return v ? v[0] : 'a';
     }();
+    // 'a' (default): the tile decoder for small inputs, the segment decoder otherwise.  A block is one serial
+    // chain for k_decode_seg's single warp (about 0.8 ms on an idle GPU); k_decode_tile puts eight warps on the
+    // block, which is the better trade when there are too few blocks to fill the machine anyway (measured, host
+    // API, 64 KiB: 1.18 -> 0.72 ms; 1 MiB: 1.40 -> 0.88 ms; 16 MiB: 2.78 vs 3.70 ms the other way round).
+    constexpr uint64_t kTileMaxBlocks = 32;
+    const char which = which_env != 'a' ? which_env : (n_blocks <= kTileMaxBlocks && d_outoff ? 't' : 's');
     if (which == 'l')
         return launch_decode_lane(d_stream, body_offset, d_offsets, n_blocks, total_out, d_out, d_status, blk_base, true,
                                   st, launches);
