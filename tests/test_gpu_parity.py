@@ -527,3 +527,24 @@ def test_streaming_file_layer(tmp_path, oracle, monkeypatch):
     want = oracle.compress(small, 0)
     hdr = len(oracle.varint_encode(small.size))
     assert got[:2].tobytes() == oracle.varint_encode(12345) and np.array_equal(got[2:], want[hdr:])
+
+
+@pytest.mark.gpu
+def test_second_device_small_bst_input(oracle):
+    """the opt-in to large dynamic shared memory is per device.  A one-block BST input takes the
+    shared-memory table tiers; it must work with cuda:1 current after cuda:0 has already been used (and the
+    host contexts are per device, so the two devices do not tear each other's buffers down)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    data = datasets.gen("corpus:text:4:0:1000")
+    want = oracle.compress(data, 1)
+    with torch.cuda.device(0):
+        _assert_same(api.snappy_compress_bst(data), want, "device 0")
+    with torch.cuda.device(1):
+        _assert_same(api.snappy_compress_bst(data), want, "device 1 (after device 0)")
+        _assert_same(api.snappy_decompress(want), data, "device 1 decode")
+        big = datasets.gen("corpus:text:4:0:300000")
+        _assert_same(api.snappy_compress_bst(big), oracle.compress(big, 1), "device 1, several blocks")
+    with torch.cuda.device(0):
+        _assert_same(api.snappy_compress(data), oracle.compress(data, 0), "device 0 again")
