@@ -412,20 +412,13 @@ __device__ __forceinline__ bool is_max_literal(const uint8_t *__restrict__ body,
            __ldg(body + q + 2) == 0xff;
 }
 
-__global__ void __launch_bounds__(128) k_group_scatter(const uint8_t *__restrict__ body, uint64_t body_len,
-                                                       uint64_t ngroup, const uint32_t *__restrict__ g_entry,
-                                                       const uint64_t *__restrict__ g_exit,
-                                                       unsigned long long *__restrict__ g_claim,
-                                                       const uint32_t *__restrict__ prev_changed)
+// What group g tells the groups after it (one round of the relaxation between groups).
+__device__ __forceinline__ void scatter_group(const uint8_t *__restrict__ body, uint64_t body_len, uint64_t ngroup,
+                                              uint64_t g, uint32_t entry, uint64_t x,
+                                              unsigned long long *__restrict__ g_claim)
 {
-    if (prev_changed && *prev_changed == 0)
-        return; // the round before changed nothing: the fixed point is reached, the rest of the batch is idle
-    const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (g >= ngroup)
-        return;
-    const bool dead = g_entry[g] & kGDead;
+    const bool dead = entry & kGDead;
     const unsigned long long prio = dead ? kLowPrio : 0ull;
-    const uint64_t x = g_exit[g];
     const uint64_t u = x / kGroupBytes; // group the chain lands in
     if (!dead) {
         // Groups jumped over hold no element start (only a live source may say so: a dead
@@ -465,6 +458,20 @@ __global__ void __launch_bounds__(128) k_group_scatter(const uint8_t *__restrict
             q = qn;
         }
     }
+}
+
+__global__ void __launch_bounds__(128) k_group_scatter(const uint8_t *__restrict__ body, uint64_t body_len,
+                                                       uint64_t ngroup, const uint32_t *__restrict__ g_entry,
+                                                       const uint64_t *__restrict__ g_exit,
+                                                       unsigned long long *__restrict__ g_claim,
+                                                       const uint32_t *__restrict__ prev_changed)
+{
+    if (prev_changed && *prev_changed == 0)
+        return; // the round before changed nothing: the fixed point is reached, the rest of the batch is idle
+    const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g >= ngroup)
+        return;
+    scatter_group(body, body_len, ngroup, g, g_entry[g], g_exit[g], g_claim);
 }
 
 __global__ void __launch_bounds__(kGroupCta) k_group_apply(const uint8_t *__restrict__ body, uint64_t body_len,
@@ -535,7 +542,8 @@ __global__ void __launch_bounds__(kGroupCta) k_group_apply32(const uint8_t *__re
                                                              unsigned long long *__restrict__ g_claim,
                                                              uint32_t *__restrict__ changed,
                                                              const uint32_t *__restrict__ prev_changed,
-                                                             uint8_t *__restrict__ entries)
+                                                             uint8_t *__restrict__ entries,
+                                                             unsigned long long *__restrict__ claim_out)
 {
     __shared__ GroupStage stage[kGroupCta / 32];
     if (prev_changed && *prev_changed == 0)
@@ -589,6 +597,14 @@ __global__ void __launch_bounds__(kGroupCta) k_group_apply32(const uint8_t *__re
             g_vis[gg] = vis;
         }
         __syncwarp();
+    }
+    // Fused: what this group tells the next round goes straight into the other claim buffer (the claims this
+    // round read are in g_claim, which every group has just reset for the round after next): one kernel per
+    // round instead of two.
+    if (claim_out && g < ngroup) {
+        __syncwarp(); // (lane 0's g_exit of a re-resolved group is visible to the lane that owns the group)
+        scatter_group(body, body_len, ngroup, g, *reinterpret_cast<volatile uint32_t *>(g_entry + g),
+                      *reinterpret_cast<volatile uint64_t *>(g_exit + g), claim_out);
     }
 }
 
@@ -864,7 +880,8 @@ size_t index_workspace_bytes(uint64_t stream_bytes)
     const uint64_t nseg = (stream_bytes + kSeg - 1) / kSeg + 1;
     const uint64_t ntile = (nseg + kScanTile - 1) / kScanTile + 1;
     const uint64_t ngroup = (nseg + kGroup - 1) / kGroup + 1;
-    return align_up(nseg * 16, 256) + 4 * align_up(nseg * 8, 256) + align_up(ntile * 8, 256) + 256 + 256 +
+    return align_up(nseg * 16, 256) + 3 * align_up(nseg * 8, 256) + align_up(std::max<uint64_t>(nseg, 128) * 8, 256) +
+           align_up(ntile * 8, 256) + 256 + 256 +
            align_up(nseg, 256) + align_up(ngroup * 4, 256) + 2 * align_up(ngroup * 8, 256) + 256;
 }
 
@@ -875,7 +892,8 @@ static IndexWorkspace carve(void *ws, uint64_t stream_bytes)
     IndexWorkspace w;
     w.paths = reinterpret_cast<uint4 *>(p), p += align_up(nseg * 16, 256);
     w.exits = reinterpret_cast<uint64_t *>(p), p += align_up(nseg * 8, 256);
-    w.claim = reinterpret_cast<unsigned long long *>(p), p += align_up(nseg * 8, 256);
+    // (two claim buffers of one entry per GROUP live here: at least 128 entries, see run_index)
+    w.claim = reinterpret_cast<unsigned long long *>(p), p += align_up(std::max<uint64_t>(nseg, 128) * 8, 256);
     w.outlen = reinterpret_cast<uint64_t *>(p), p += align_up(nseg * 8, 256);
     w.outoff = reinterpret_cast<uint64_t *>(p), p += align_up(nseg * 8, 256);
     w.total = reinterpret_cast<uint64_t *>(p), p += 256;
@@ -950,21 +968,40 @@ cudaError_t run_index(const uint8_t *d_stream, uint64_t stream_bytes, uint64_t b
     // a chain over ngroup groups is resolved after at most ngroup rounds (one more shows that nothing moves):
     // small streams do not pay for a full batch of launches
     batch = (uint32_t)std::min<uint64_t>(batch, ngroup + 1);
+    // Two claim buffers: round 0 is scatter + k_group_apply (one warp per group: the first round moves most
+    // groups); from round 1 on one fused kernel per round applies the claims of one buffer and scatters those of
+    // the next round into the other.  SNAPPY_B200_K0_UNFUSED=1 keeps the two-kernel rounds (A/B).
+    static const bool unfused = getenv("SNAPPY_B200_K0_UNFUSED") != nullptr;
+    unsigned long long *claim[2] = {w.claim, w.claim + align_up(ngroup + 1, 32)};
+    if ((e = cudaMemsetAsync(claim[1], 0xff, (ngroup + 1) * 8, st)) != cudaSuccess) // kNone
+        return e;
+    int cur = 0; // buffer that holds the claims of the next round to apply (from round 1 on)
     for (uint64_t round = 0;;) {
         if ((e = cudaMemsetAsync(w.changed, 0, 4 * kMaxBatch, st)) != cudaSuccess)
             return e;
         for (uint32_t k = 0; k < batch; ++k) {
             const uint32_t *prev = k ? w.changed + k - 1 : nullptr;
-            k_group_scatter<<<ggrid, 128, 0, st>>>(body, body_len, ngroup, w.g_entry, w.g_exit, w.claim, prev);
-            if (round + k == 0) // the first round moves most groups: one warp each
+            if (round + k == 0) {
+                k_group_scatter<<<ggrid, 128, 0, st>>>(body, body_len, ngroup, w.g_entry, w.g_exit, claim[0], nullptr);
                 k_group_apply<<<wgrid, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits, w.g_entry,
-                                                           w.g_exit, w.g_vis, w.claim, w.changed + k, w.entry);
-            else
+                                                           w.g_exit, w.g_vis, claim[0], w.changed + k, w.entry);
+                if (!unfused) // the claims of round 1
+                    k_group_scatter<<<ggrid, 128, 0, st>>>(body, body_len, ngroup, w.g_entry, w.g_exit, claim[0], nullptr);
+                *launches += 3;
+            } else if (unfused) {
+                k_group_scatter<<<ggrid, 128, 0, st>>>(body, body_len, ngroup, w.g_entry, w.g_exit, claim[0], prev);
                 k_group_apply32<<<wgrid32, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits,
-                                                               w.g_entry, w.g_exit, w.g_vis, w.claim, w.changed + k,
-                                                               prev, w.entry);
+                                                               w.g_entry, w.g_exit, w.g_vis, claim[0], w.changed + k,
+                                                               prev, w.entry, nullptr);
+                *launches += 2;
+            } else {
+                k_group_apply32<<<wgrid32, kGroupCta, 0, st>>>(body, body_len, nseg, ngroup, w.paths, w.exits,
+                                                               w.g_entry, w.g_exit, w.g_vis, claim[cur], w.changed + k,
+                                                               prev, w.entry, claim[cur ^ 1]);
+                cur ^= 1;
+                *launches += 1;
+            }
         }
-        *launches += 2 * batch;
         if (fixed_rounds) {
             unresolved = w.changed + batch - 1;
             break;
