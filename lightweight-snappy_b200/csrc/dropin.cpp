@@ -141,7 +141,7 @@ const char kIndexMagic[8] = {'S', 'N', 'P', 'I', 'D', 'X', '1', 0};
 
 // The streaming compressor behind snappy_compress / snappy_compress_bst.  The reference works through the file
 // 64 KiB at a time (src/snappy_compression.c:210-213, :419-425); here the unit is a chunk of whole blocks
-// (64 MiB per device in use): a reader thread fills page-locked input buffers, the calling thread runs the
+// (32 MiB per device in use): a reader thread fills page-locked input buffers, the calling thread runs the
 // GPU pipeline on one chunk while the next is being read, a writer thread appends the finished chunks.
 // Three chunks are in flight, so page-locked memory is bounded by the chunk size, not by the file size.
 struct ChunkQueue { // hands slot numbers from one thread to the next
@@ -168,7 +168,7 @@ struct ChunkQueue { // hands slot numbers from one thread to the next
 
 uint64_t stream_chunk_bytes(unsigned long long declared)
 {
-    uint64_t mib = 64;
+    uint64_t mib = 32; // (page-locking costs ~45 ms per 32 MiB buffer and there are six: a cold command line pays it)
     if (const char *v = getenv("SNAPPY_B200_FILE_CHUNK_MIB"))
         mib = (uint64_t)std::max(1ll, atoll(v));
     uint64_t dev = 1;
