@@ -167,11 +167,21 @@ def test_roundtrip_properties_at_scale():
     assert torch.equal(b1, b2)
     ratio = n / s1.numel()
     assert 1.5 < ratio < 4.0, ratio
+    # and against the oracle: 32 blocks spread over the 256 MiB, byte for byte
+    import oracle_lib
+    orc = oracle_lib.Oracle()
+    offs = offs1.cpu().numpy()
+    for b in np.linspace(0, n // 65536 - 1, 32).astype(np.int64):
+        blk = data[b * 65536:(b + 1) * 65536].cpu().numpy()
+        ref = orc.compress(blk, 0)
+        vl = len(orc.varint_encode(blk.size))
+        got = s1[int(offs[b]):int(offs[b + 1])].cpu().numpy()
+        _assert_same(got, ref[vl:], f"block {b} vs oracle")
 
 
-def test_host_pipeline_many_chunks(monkeypatch):
-    """The chunked host pipeline (3 compress chunks, 4 upload pieces, a ragged tail) gives the
-    same stream as one device-resident call, from pageable and from page-locked buffers."""
+def test_host_pipeline_many_chunks(monkeypatch, oracle):
+    """The chunked host pipeline (13 compress chunks, ~15 upload pieces, a ragged tail) gives the
+    ORACLE's stream (and so does one device-resident call), from pageable and from page-locked buffers."""
     import torch
     monkeypatch.setenv("SNAPPY_B200_CHUNK_MIB", "16")   # 13 compress chunks, 4 in flight
     monkeypatch.setenv("SNAPPY_B200_PIECE_MIB", "8")    # ~15 upload pieces
@@ -179,8 +189,10 @@ def test_host_pipeline_many_chunks(monkeypatch):
     data = corpus.make_corpus("mixed", n, device="cuda", first_segment=7)
     codec = api.DeviceCodec(n)
     codec.compress(data, 0)
-    want = codec.result_stream().cpu().numpy()
     host = data.cpu()
+    want = oracle.compress(host.numpy(), 0)
+    _assert_same(codec.result_stream().cpu().numpy(), want, "device-resident stream vs oracle")
+    _assert_same(oracle.decompress(want), host.numpy(), "oracle decoder on the stream")
     pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     pinned.copy_(host)
     for src in (host.numpy(), pinned.numpy()):
